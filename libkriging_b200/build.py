@@ -1,0 +1,49 @@
+"""Build liblkgpu.so (the C-ABI engine of include/lkgpu.h) in-tree with nvcc for sm_100a.
+
+    python -m libkriging_b200.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "liblkgpu.so")
+SOURCES = ["engine.cu"]
+HEADERS = ["common.cuh", "cov.cuh", "gemm_dmma.cuh", "potrf_panel.cuh", "trsv.cuh", "lmp_loo.cuh", "objective.inl",
+           os.path.join("..", "..", "include", "lkgpu.h")]
+
+
+def needs_build() -> bool:
+    if not os.path.isfile(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for f in SOURCES + HEADERS + [os.path.join("..", "build.py")]:
+        fp = os.path.join(CSRC, f)
+        if os.path.isfile(fp) and os.path.getmtime(fp) > t:
+            return True
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building liblkgpu.so")
+    if verbose:
+        sys.stderr.write(r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
