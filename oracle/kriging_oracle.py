@@ -470,6 +470,8 @@ def predict(pb: Problem, theta, sigma2, Xn, Fn, m: KModel | None = None):
     R_on = corr_from_dx(dx, np.asarray(theta, float), pb.kernel)
     if pb.noise_model == "nugget":
         R_on = R_on * pb.alpha
+    # coincident points: exactly 1, no R_on_factor (KrigingImpl.cpp:199-202, dij.is_zero(eps))
+    R_on = np.where(np.all(np.abs(dx) <= np.finfo(float).eps, axis=-1), 1.0, R_on)
     Rstar_on = solve_lower(m.L, R_on)
     z = m.Estar
     mean = Fn @ m.betahat + Rstar_on.T @ z
