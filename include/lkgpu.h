@@ -142,6 +142,9 @@ const char* lkgpu_last_error(void);
 int lkgpu_abi_version(void);
 /* number of kernels launched by this handle since creation (bench.py "gpu_launches") */
 long long lkgpu_launch_count(void* handle);
+/* the CUDA stream (cudaStream_t) every kernel of this handle is launched on; bench.py records its
+ * CUDA events on it.  The main stream is non-blocking with respect to the legacy default stream. */
+void* lkgpu_get_stream(void* handle);
 /* FP64 DMMA peak probe (dependent-free mma.sync.m8n8k4.f64 chains on every SM):
  * returns TFLOP/s in *tflops.  Used by bench.py for the roofline denominator. */
 int lkgpu_probe_fp64_peak(int device, int mode, double* tflops);

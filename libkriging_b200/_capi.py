@@ -68,6 +68,8 @@ def lib():
     L.lkgpu_abi_version.restype = C.c_int
     L.lkgpu_launch_count.argtypes = [vp]
     L.lkgpu_launch_count.restype = C.c_longlong
+    L.lkgpu_get_stream.argtypes = [vp]
+    L.lkgpu_get_stream.restype = C.c_void_p
     L.lkgpu_probe_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
     _lib = L
     return L
@@ -183,6 +185,11 @@ class Engine:
         var = np.empty(m) if want_var else None
         _check(lib().lkgpu_predict(self._h, m, _ptr(Xn), _ptr(Fn), _ptr(beta), float(r_on_factor), _ptr(mean), _ptr(var)))
         return mean, var
+
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t of the handle's launch stream (for CUDA-event timing by the caller)."""
+        return int(lib().lkgpu_get_stream(self._h) or 0)
 
     @property
     def launch_count(self) -> int:

@@ -1130,6 +1130,8 @@ void lkgpu_destroy(void* handle) {
   if (handle) delete static_cast<Engine*>(handle);
 }
 
+void* lkgpu_get_stream(void* handle) { return handle ? (void*)static_cast<Engine*>(handle)->s_main : nullptr; }
+
 long long lkgpu_launch_count(void* handle) { return handle ? static_cast<Engine*>(handle)->launches : 0; }
 
 int lkgpu_probe_fp64_peak(int device, int mode, double* tflops) {

@@ -131,6 +131,9 @@ int main(int argc, char** argv) {
       times.push_back(now_s() - t1);
       val = std::get<0>(res); grad = std::get<1>(res);
     }
+    js << "\"eval_s_all\": [";
+    for (size_t i = 0; i < times.size(); i++) js << (i ? ", " : "") << times[i];
+    js << "], ";
     std::sort(times.begin(), times.end());
     js.precision(17);
     js << "\"value\": " << std::scientific << val << ", ";
