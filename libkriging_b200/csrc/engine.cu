@@ -22,6 +22,7 @@
 #include "gemm_dmma.cuh"
 #include "potrf_panel.cuh"
 #include "trsv.cuh"
+#include "trsv_wave.cuh"
 
 using namespace lk;
 
@@ -59,14 +60,16 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 // 2D map over a column-major N x ncols fp64 matrix: dim0 = rows (contiguous), dim1 = columns.
-CUtensorMap make_map(double* base, long long rows, long long cols, long long ld, int box_rows, int box_cols) {
+CUtensorMap make_map(double* base, long long rows, long long cols, long long ld, int box_rows, int box_cols,
+                     bool swizzle128 = true) {
   CUtensorMap m;
   cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
   cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw LkError{"cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)};
   return m;
@@ -75,6 +78,8 @@ CUtensorMap make_map(double* base, long long rows, long long cols, long long ld,
 struct MatMaps {
   CUtensorMap mm;  // M-major operand tiles: box {16 rows, 16 k-columns}
   CUtensorMap km;  // K-major operand tiles: box {16 k-rows, 64 columns}
+  CUtensorMap wf;  // wavefront sweep, forward: box {128 rows, 32 columns}, dense
+  CUtensorMap wb;  // wavefront sweep, backward: box {16 rows, 128 columns}, SWIZZLE_128B
 };
 
 // FP64 peak probe kernels ---------------------------------------------------
@@ -159,6 +164,8 @@ struct Engine {
   int sm_count = 148;
   bool debug_simple = false;
   bool use_lookahead = true;
+  bool use_step_trsv = false;
+  int outer_panels = 4;  // Cholesky outer block = outer_panels * 128 columns (LKGPU_OUTER_PANELS)
   // numerics (LinearAlgebra statics of the reference)
   double num_nugget = 1e-10, min_rcond = 1e-18;
   int max_inc = 10;
@@ -182,6 +189,7 @@ struct Engine {
   bool have_loo = false;
   double* logdet_blocks = nullptr;
   int* dinfo = nullptr;       // [0] chol info, [1] gls info
+  int* wave_ctl = nullptr;    // wavefront sweeps: [0] ticket counter, [1 + i] flag of row block i
   double* dscal = nullptr;    // small device scalars / results (64 doubles)
   double* dpartial = nullptr; // reduction partials
   size_t partial_doubles = 0;
@@ -215,6 +223,8 @@ struct Engine {
     for (double* b : bufs)
       if (b) cudaFree(b);
     if (dinfo) cudaFree(dinfo);
+    if (wave_ctl) cudaFree(wave_ctl);
+    wave_ctl = nullptr;
     if (trtri_tables) cudaFree(trtri_tables);
     if (lauum_table) cudaFree(lauum_table);
     if (loo_table) cudaFree(loo_table);
@@ -269,6 +279,9 @@ struct Engine {
     debug_simple = dbg && dbg[0] == '1';
     const char* nla = getenv("LKGPU_NO_LOOKAHEAD");
     use_lookahead = !(nla && nla[0] == '1');
+    if (const char* op = getenv("LKGPU_OUTER_PANELS")) outer_panels = std::max(1, std::min(16, atoi(op)));
+    const char* stv = getenv("LKGPU_STEP_TRSV");
+    use_step_trsv = stv && stv[0] == '1';
 
     N = ((n + BLK - 1) / BLK) * BLK;
     nb = N / BLK;
@@ -323,9 +336,19 @@ struct Engine {
     CUDA_CHECK(cudaMemsetAsync(A, 0, (size_t)N * N * 8, s_main));
     set_data(X, y, F, noise);
 
-    mapA = {make_map(A, N, N, ld, 16, 16), make_map(A, N, N, ld, 16, 64)};
-    mapW = {make_map(W, N, N, ld, 16, 16), make_map(W, N, N, ld, 16, 64)};
-    mapV = {make_map(V, N, N, ld, 16, 16), make_map(V, N, N, ld, 16, 64)};
+    auto maps_of = [&](double* buf) {
+      return MatMaps{make_map(buf, N, N, ld, 16, 16), make_map(buf, N, N, ld, 16, 64),
+                     make_map(buf, N, N, ld, 128, 32, false), make_map(buf, N, N, ld, 16, 128)};
+    };
+    mapA = maps_of(A);
+    mapW = maps_of(W);
+    mapV = maps_of(V);
+    wave_ctl = dalloc<int>(nb + 1);
+#define LK_WAVE_ATTR(BW, NQ_) \
+  CUDA_CHECK(cudaFuncSetAttribute(trsv_wave_kernel<BW, NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_smem_bytes(NQ_)))
+    LK_WAVE_ATTR(false, 1); LK_WAVE_ATTR(false, 2); LK_WAVE_ATTR(false, 4); LK_WAVE_ATTR(false, 8);
+    LK_WAVE_ATTR(true, 1); LK_WAVE_ATTR(true, 2); LK_WAVE_ATTR(true, 4); LK_WAVE_ATTR(true, 8);
+#undef LK_WAVE_ATTR
 
     CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -465,41 +488,56 @@ struct Engine {
     CUDA_CHECK(cudaGetLastError());
   }
 
-  // ---- blocked right-looking Cholesky with one-step look-ahead (a3) ----
+  // ---- two-level blocked right-looking Cholesky with look-ahead (a3) ----
+  // Outer blocks of `outer_panels` 128-column panels.  Inside an outer block every panel is factored (POTF2 +
+  // inverse), its column is solved (TRSM as a GEMM with the inverse) and only the REST OF THE OUTER BLOCK is
+  // updated (k = 128).  The trailing matrix is then updated once per outer block with k = 128 * outer_panels:
+  // 1/outer_panels of the C read-modify-write traffic and main loops long enough to fill the DMMA pipe.
+  // Look-ahead: the next outer block's columns are updated first on the high-priority stream, which then factors
+  // them while the low-priority stream updates the rest of the trailing matrix.
+  GemmArgs trap_args(int row0, int mt, int ncols, int k0, int k1) {
+    GemmArgs a = rect_args(A, EPI_SUB, row0, row0, mt, ncols, k0, k1);
+    a.sched = SCHED_TRAP;
+    a.ntiles = ncols * mt - ncols * (ncols - 1);
+    return a;
+  }
   void cholesky() {
     CUDA_CHECK(cudaMemsetAsync(dinfo, 0, 4 * sizeof(int), s_main));
+    const int OB = outer_panels;
     int last_upd = -1;
-    for (int j = 0; j < nb; ++j) {
-      const int jb = j * BLK;
-      ++launches;
-      potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM_BYTES, s_main>>>(A, W, ld, jb, logdet_blocks, j, dinfo);
-      CUDA_CHECK(cudaGetLastError());
-      const int rem = nb - j - 1;
-      if (rem == 0) break;
-      // panel TRSM as GEMM with the inverted diagonal block: A[i, j] <- A[i, j] * Dinv_j^T  (in place)
-      gemm(0, mapA, A, mapW, W, rect_args(A, EPI_SET, jb + BLK, jb, 2 * rem, 1, jb, jb + BLK), s_main, false);
-      if (use_lookahead && rem > 1) {
-        CUDA_CHECK(cudaEventRecord(ev_panel[j], s_main));
+    for (int J0 = 0; J0 < nb; J0 += OB) {
+      const int J1 = std::min(nb, J0 + OB);
+      const int c0 = J0 * BLK, c1 = J1 * BLK;
+      for (int j = J0; j < J1; ++j) {
+        const int jb = j * BLK;
+        ++launches;
+        potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM_BYTES, s_main>>>(A, W, ld, jb, logdet_blocks, j, dinfo);
+        CUDA_CHECK(cudaGetLastError());
+        const int rem = nb - j - 1;
+        if (rem == 0) break;
+        // panel TRSM as GEMM with the inverted diagonal block: A[i, j] <- A[i, j] * Dinv_j^T  (in place)
+        gemm(0, mapA, A, mapW, W, rect_args(A, EPI_SET, jb + BLK, jb, 2 * rem, 1, jb, jb + BLK), s_main, false);
+        const int ncol = J1 - (j + 1);  // panels of this outer block still to be factored
+        if (ncol > 0) gemm(0, mapA, A, mapA, A, trap_args(jb + BLK, 2 * rem, ncol, jb, jb + BLK), s_main, false);
+      }
+      const int rem = nb - J1;  // panels after this outer block
+      if (rem <= 0) break;
+      if (use_lookahead && rem > OB) {
+        CUDA_CHECK(cudaEventRecord(ev_panel[J0], s_main));
         if (last_upd >= 0) CUDA_CHECK(cudaStreamWaitEvent(s_main, ev_upd[last_upd], 0));
-        // look-ahead: update block column j+1 first (on the panel stream) ...
-        gemm(0, mapA, A, mapA, A, rect_args(A, EPI_SUB, jb + BLK, jb + BLK, 2 * rem, 1, jb, jb + BLK), s_main, false);
-        // ... while the rest of the trailing matrix is updated on the low-priority stream
-        CUDA_CHECK(cudaStreamWaitEvent(s_upd, ev_panel[j], 0));
-        GemmArgs a = rect_args(A, EPI_SUB, jb + 2 * BLK, jb + 2 * BLK, 2 * (rem - 1), rem - 1, jb, jb + BLK);
-        a.sched = SCHED_TRAP;
-        a.ntiles = (rem - 1) * (rem - 1) + (rem - 1);
-        gemm(0, mapA, A, mapA, A, a, s_upd, false);
-        CUDA_CHECK(cudaEventRecord(ev_upd[j], s_upd));
-        last_upd = j;
+        // look-ahead: the next outer block's columns first, on the factorisation stream ...
+        gemm(0, mapA, A, mapA, A, trap_args(c1, 2 * rem, OB, c0, c1), s_main, false);
+        // ... the rest of the trailing matrix on the low-priority stream
+        CUDA_CHECK(cudaStreamWaitEvent(s_upd, ev_panel[J0], 0));
+        gemm(0, mapA, A, mapA, A, trap_args(c1 + OB * BLK, 2 * (rem - OB), rem - OB, c0, c1), s_upd, false);
+        CUDA_CHECK(cudaEventRecord(ev_upd[J0], s_upd));
+        last_upd = J0;
       } else {
         if (last_upd >= 0) {
           CUDA_CHECK(cudaStreamWaitEvent(s_main, ev_upd[last_upd], 0));
           last_upd = -1;
         }
-        GemmArgs a = rect_args(A, EPI_SUB, jb + BLK, jb + BLK, 2 * rem, rem, jb, jb + BLK);
-        a.sched = SCHED_TRAP;
-        a.ntiles = rem * rem + rem;
-        gemm(0, mapA, A, mapA, A, a, s_main, false);
+        gemm(0, mapA, A, mapA, A, trap_args(c1, 2 * rem, rem, c0, c1), s_main, false);
       }
     }
     if (last_upd >= 0) CUDA_CHECK(cudaStreamWaitEvent(s_main, ev_upd[last_upd], 0));
@@ -543,7 +581,38 @@ struct Engine {
   }
 
   // ---- triangular sweeps (a5) ----
+  template <bool BWD>
+  void solve_wave(double* B, int nrhs) {
+    const int grid = std::min(nb, sm_count);
+    for (int q0 = 0; q0 < nrhs; q0 += WAVE_MAX_RHS) {
+      const int nq = std::min(WAVE_MAX_RHS, nrhs - q0);
+      double* Bq = B + (long long)q0 * N;
+      CUDA_CHECK(cudaMemsetAsync(wave_ctl, 0, (size_t)(nb + 1) * sizeof(int), s_main));
+      ++launches;
+      const CUtensorMap& mL = BWD ? mapA.wb : mapA.wf;
+      const CUtensorMap& mW = BWD ? mapW.wb : mapW.wf;
+      if (nq == 1)
+        trsv_wave_kernel<BWD, 1><<<grid, WAVE_THREADS, wave_smem_bytes(1), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl);
+      else if (nq == 2)
+        trsv_wave_kernel<BWD, 2><<<grid, WAVE_THREADS, wave_smem_bytes(2), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl);
+      else if (nq <= 4)
+        trsv_wave_kernel<BWD, 4><<<grid, WAVE_THREADS, wave_smem_bytes(4), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl);
+      else
+        trsv_wave_kernel<BWD, 8><<<grid, WAVE_THREADS, wave_smem_bytes(8), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl);
+      CUDA_CHECK(cudaGetLastError());
+    }
+  }
+  // ---- triangular sweeps (a5): one persistent wavefront kernel per sweep (trsv_wave.cuh) ----
   void solve_fwd(double* B, int nrhs) {
+    if (use_step_trsv) return solve_fwd_steps(B, nrhs);
+    solve_wave<false>(B, nrhs);
+  }
+  void solve_bwd(double* B, int nrhs) {
+    if (use_step_trsv) return solve_bwd_steps(B, nrhs);
+    solve_wave<true>(B, nrhs);
+  }
+  // launch-chain variant (one kernel per 128-row step), kept for fault localisation: LKGPU_STEP_TRSV=1
+  void solve_fwd_steps(double* B, int nrhs) {
     for (int q0 = 0; q0 < nrhs; q0 += TRSV_MAX_RHS) {
       const int nq = std::min(TRSV_MAX_RHS, nrhs - q0);
       double* Bq = B + (long long)q0 * N;
@@ -554,7 +623,7 @@ struct Engine {
       CUDA_CHECK(cudaGetLastError());
     }
   }
-  void solve_bwd(double* B, int nrhs) {
+  void solve_bwd_steps(double* B, int nrhs) {
     for (int q0 = 0; q0 < nrhs; q0 += TRSV_MAX_RHS) {
       const int nq = std::min(TRSV_MAX_RHS, nrhs - q0);
       double* Bq = B + (long long)q0 * N;

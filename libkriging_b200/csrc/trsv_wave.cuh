@@ -1,0 +1,204 @@
+// trsv_wave.cuh -- wavefront triangular sweeps (reference solve_lower / solve_upper,
+// src/lib/LinearAlgebra.cpp:695-701, called at src/lib/KrigingImpl.cpp:102-103, 122 and src/lib/Kriging.cpp:294).
+//
+// One persistent kernel per sweep replaces the nb-step launch chain.  The sweep is HBM-bound (4 n^2 bytes of L
+// per sweep, a few right-hand sides), and its only serial part is the chain z_0 -> z_1 -> ... of 128-row blocks:
+//   forward  (L z = b):    z_i = Dinv_i (b_i - sum_{j<i} L[i,j] z_j)
+//   backward (L^T x = e):  x_k = Dinv_k^T (e_k - sum_{j>k} L[j,k]^T x_j)
+// Dinv_i = inverse of L's diagonal block, kept in W's diagonal blocks by the panel kernel (and still there after
+// TRTRI: the diagonal blocks of L^-1 are the inverses of the diagonal blocks of L).
+//
+// CTAs take row blocks from a ticket counter in sweep order, so a CTA only ever waits on blocks owned by CTAs
+// that are already resident (no deadlock for any grid size).  Each CTA streams ITS row (column) of 128 x 128
+// tiles through a TMA ring as fast as HBM delivers them -- L is read-only, so the prefetch never waits -- and
+// consumes tile j as soon as the flag of z_j is published (st.release / ld.acquire at gpu scope).  The serial
+// chain per block is then: see flag -> one tile product -> one Dinv product -> publish  (~3-4 us).
+//
+// Tile traffic: forward uses boxes {128 rows, 32 cols} (dense, thread <-> row: conflict-free LDS.64),
+// backward uses boxes {16 rows, 128 cols} with SWIZZLE_128B (thread <-> column: conflict-free LDS.128).
+#pragma once
+#include "common.cuh"
+
+namespace lk {
+
+constexpr int WAVE_COMPUTE_THREADS = 256;
+constexpr int WAVE_THREADS = WAVE_COMPUTE_THREADS + 32;  // + 1 TMA producer warp
+constexpr int WAVE_STAGES = 6;
+constexpr int WAVE_STAGE_BYTES = 32768;  // fwd: one {128 x 32} box ; bwd: two {16 x 128} boxes
+constexpr int WAVE_SUBTILES = 4;         // sub-tiles (stages) per 128 x 128 tile
+constexpr int WAVE_MAX_RHS = 8;
+
+__host__ __device__ constexpr int wave_smem_bytes(int nq) {
+  return WAVE_STAGES * WAVE_STAGE_BYTES + 1024 /*align*/ + 3 * nq * 128 * 8 /*vec + 2 partials*/ + 256 /*barriers*/;
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void bar_sync_compute() {
+  asm volatile("bar.sync 1, %0;" ::"n"(WAVE_COMPUTE_THREADS) : "memory");
+}
+
+// ctl[0] = ticket counter, ctl[1 + i] = flag of row block i (zeroed by the host before each launch).
+template <bool BWD, int NQ>
+__global__ void __launch_bounds__(WAVE_THREADS, 1)
+trsv_wave_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constant__ CUtensorMap tmapW,
+                 double* __restrict__ B, long long ldb, int nrhs, int nb, int* __restrict__ ctl) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  double* vec = reinterpret_cast<double*>(ring + WAVE_STAGES * WAVE_STAGE_BYTES);  // [NQ][128] current z_j / t
+  double* part = vec + NQ * 128;                                                   // [2][NQ][128] partials
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + 2 * NQ * 128);
+  uint64_t* empty_bar = full_bar + WAVE_STAGES;
+  __shared__ int s_ticket;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp == WAVE_COMPUTE_THREADS / 32;
+  if (tid == 0) {
+    for (int s = 0; s < WAVE_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], WAVE_COMPUTE_THREADS / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (producer && lane == 0) {
+    tma_prefetch_desc(&tmapL);
+    tma_prefetch_desc(&tmapW);
+  }
+  int* flags = ctl + 1;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  while (true) {
+    if (tid == 0) s_ticket = atomicAdd(ctl, 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    __syncthreads();
+    if (ticket >= nb) break;
+    const int i = BWD ? (nb - 1 - ticket) : ticket;  // this CTA's row block
+    const int ntiles = ticket + 1;                   // off-diagonal tiles in sweep order, then the Dinv tile
+    const int ib = i * 128;
+
+    if (producer) {
+      if (lane == 0) {
+        for (int tq = 0; tq < ntiles; ++tq) {
+          const bool diag = (tq == ntiles - 1);
+          const int j = BWD ? (nb - 1 - tq) : tq;  // for the last tile j == i
+          const CUtensorMap* map = diag ? &tmapW : &tmapL;
+          for (int s = 0; s < WAVE_SUBTILES; ++s) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* dst = ring + stage * WAVE_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], WAVE_STAGE_BYTES);
+            if (!BWD) {
+              // tile rows = block i, cols = block j : box {128 rows, 32 cols} at (row ib, col 128 j + 32 s)
+              tma_load_2d(dst, map, &full_bar[stage], ib, j * 128 + 32 * s);
+            } else {
+              // tile rows = block j, cols = block i : two boxes {16 rows, 128 cols} at rows 128 j + 32 s (+16)
+              tma_load_2d(dst, map, &full_bar[stage], j * 128 + 32 * s, ib);
+              tma_load_2d(dst + 16384, map, &full_bar[stage], j * 128 + 32 * s + 16, ib);
+            }
+            if (++stage == WAVE_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      continue;  // producer warp goes back for the next ticket
+    }
+
+    // ============================ compute threads ============================
+    const int r = tid & 127, h = tid >> 7;
+    double acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = (h == 0 && q < nrhs) ? B[q * ldb + ib + r] : 0.0;
+
+    for (int tq = 0; tq < ntiles; ++tq) {
+      const bool diag = (tq == ntiles - 1);
+      if (!diag) {
+        const int j = BWD ? (nb - 1 - tq) : tq;
+        if (tid == 0) {
+          while (ld_acquire_gpu(flags + j) == 0) {
+          }
+        }
+        bar_sync_compute();
+        if (tid < 128) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) vec[q * 128 + tid] = (q < nrhs) ? __ldcg(B + q * ldb + j * 128 + tid) : 0.0;
+        }
+        bar_sync_compute();
+      } else {
+        // t = b_i - sum(...) : combine the two half-sums, negate-free (acc already holds b - sum), then restart
+        bar_sync_compute();
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) part[(h * NQ + q) * 128 + r] = acc[q];
+        bar_sync_compute();
+        if (h == 0) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) vec[q * 128 + r] = part[q * 128 + r] + part[(NQ + q) * 128 + r];
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+        bar_sync_compute();
+      }
+      const double sgn = diag ? 1.0 : -1.0;
+      for (int s = 0; s < WAVE_SUBTILES; ++s) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* tile = ring + stage * WAVE_STAGE_BYTES;
+        if (!BWD) {
+          // thread (r, h): row r, columns 16 h .. 16 h + 15 of this 32-column sub-tile
+          const double* tp = reinterpret_cast<const double*>(tile) + (h * 16) * 128 + r;
+          const double* vp = vec + 32 * s + 16 * h;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const double a = sgn * tp[c * 128];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[q] = fma(a, vp[q * 128 + c], acc[q]);
+          }
+        } else {
+          // thread (c = r, h): column c, rows 16 h .. 16 h + 15 of this 32-row sub-tile (box h, 8 chunks of 16 B)
+          const uint8_t* line = tile + h * 16384 + r * 128;
+          const double* vp = vec + 32 * s + 16 * h;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const double2 a = *reinterpret_cast<const double2*>(line + ((ch ^ (r & 7)) << 4));
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              acc[q] = fma(sgn * a.x, vp[q * 128 + 2 * ch], acc[q]);
+              acc[q] = fma(sgn * a.y, vp[q * 128 + 2 * ch + 1], acc[q]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == WAVE_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    // z_i = sum of the two half-products of the Dinv tile
+    bar_sync_compute();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) part[(h * NQ + q) * 128 + r] = acc[q];
+    bar_sync_compute();
+    if (h == 0) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (q < nrhs) __stcg(B + q * ldb + ib + r, part[q * 128 + r] + part[(NQ + q) * 128 + r]);
+      __threadfence();
+    }
+    bar_sync_compute();
+    if (tid == 0) st_release_gpu(flags + i, 1);
+  }
+}
+
+}  // namespace lk
