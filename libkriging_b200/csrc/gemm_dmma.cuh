@@ -1,17 +1,17 @@
 // gemm_dmma.cuh -- the FP64 tensor-core tile engine behind Cholesky's trailing
 // update (SYRK), the panel TRSM, TRTRI and LAUUM.
 //
-// One persistent, warp-specialised kernel:
-//   * 1 producer warp: one elected lane issues TMA (cp.async.bulk.tensor.2d,
-//     SWIZZLE_128B) loads of the two operand tiles of each k-stage into a
-//     4-deep shared-memory ring guarded by full/empty mbarriers, running ahead
-//     across tile boundaries;
-//   * 4 consumer warps: each owns a 64(row) x 32(col) slab of the 64 x 128
-//     output tile as 32 independent m8n8k4 FP64 accumulators (DMMA.8x8x4),
-//     reads its fragments conflict-free from the swizzled tiles, and applies
-//     the epilogue (C = acc | C = -acc | C -= acc) with 16-byte accesses.
-// Two CTAs fit per SM (96 KB smem, <= 168 regs) so one CTA's epilogue overlaps
-// the other's main loop.
+// One persistent kernel, four warps per CTA, two CTAs per SM (96 KB smem each):
+//   * thread 0 is the TMA producer, inline in warp 0's loop: it issues the cp.async.bulk.tensor.2d
+//     (SWIZZLE_128B) loads of the two operand tiles of k-stage c+3 just before the CTA consumes k-stage c,
+//     into a 4-deep shared-memory ring guarded by full/empty mbarriers, running ahead across tile boundaries.
+//     (A producer-only fifth warp would put three warps on one SM sub-partition and cap every thread at
+//     168 registers -- measured: spills in the main loop; with 2 warps per sub-partition the kernel uses ~210.)
+//   * all four warps are consumers: each owns a 64(row) x 32(col) slab of the 64 x 128 output tile as 32
+//     independent m8n8k4 FP64 accumulators (DMMA.8x8x4), reads its fragments conflict-free from the swizzled
+//     tiles with register + immediate addressing, software-pipelined one k-step ahead, and applies the
+//     epilogue (C = acc | C = -acc | C -= acc) with 16-byte accesses.
+// One CTA's epilogue overlaps the other CTA's main loop.
 //
 // All matrices are column-major doubles with dimensions padded to 128.
 //   C[c_row + m, c_col + n] (op)= sum_{k in [k_begin, k_end)} Ms(m, k) * Ns(n, k)
@@ -34,7 +34,7 @@ constexpr int TN = 128;      // C cols per tile
 constexpr int TK = 16;       // k per pipeline stage (16 doubles = one 128-byte swizzle row)
 constexpr int GSTAGES = 4;   // pipeline depth
 constexpr int GEMM_CONSUMER_WARPS = 4;
-constexpr int GEMM_THREADS = 32 * (GEMM_CONSUMER_WARPS + 1);
+constexpr int GEMM_THREADS = 32 * GEMM_CONSUMER_WARPS;  // the TMA producer is thread 0 of consumer warp 0
 constexpr int NS_TILE_BYTES = TN * TK * 8;  // 16384
 constexpr int MS_TILE_BYTES = TM * TK * 8;  // 8192
 constexpr int STAGE_BYTES = NS_TILE_BYTES + MS_TILE_BYTES;
@@ -100,6 +100,61 @@ __device__ __forceinline__ uint32_t tile_off(int r, int kk) {
   }
 }
 
+// ---- fragment addressing -------------------------------------------------------------------------------
+// Byte offset of element (row, kk) of an operand tile = R[sel(s, idx)] + imm(s, idx), where row = 8 idx + g
+// (+ 32 warp on the N side, folded into R by init's side_base), kk is lane t's k index in k-step s, R[] are
+// per-lane registers and imm is a compile-time constant (it becomes the LDS immediate).
+template <bool KMAJ, bool BOTHK>
+struct FragAddr {
+  uint32_t R[4];
+  __device__ __forceinline__ void init(int g, int t, uint32_t side_base) {
+    if (!KMAJ) {
+      // M-major: off = ((row>>4)*16 + kk)*128 + ((((row&15)>>1) ^ (kk&7)) << 4 | (row&1) << 3), kk = 2t + (s&1) + 8(s>>1)
+#pragma unroll
+      for (int sel = 0; sel < 4; ++sel) {
+        const int sp = sel >> 1, ip = sel & 1;
+        const int kk7 = 2 * t + sp;
+        R[sel] = side_base + (uint32_t)(kk7 * 128 + ((((ip * 4 + (g >> 1)) ^ kk7) << 4) | ((g & 1) << 3)));
+      }
+    } else if (!BOTHK) {
+      // K-major beside an M-major operand: off = row*128 + (((kk>>1) ^ (row&7)) << 4 | (kk&1) << 3), same kk
+#pragma unroll
+      for (int sel = 0; sel < 4; ++sel) R[sel] = side_base + (uint32_t)(g * 128 + ((((t + 4 * (sel & 1)) ^ g) << 4)));
+    } else {
+      // both K-major: kk = 2s + (t&1) + 8(t>>1)
+#pragma unroll
+      for (int sel = 0; sel < 4; ++sel)
+        R[sel] = side_base + (uint32_t)(g * 128 + ((((sel + 4 * (t >> 1)) ^ g) << 4) | ((t & 1) << 3)));
+    }
+  }
+};
+template <bool KMAJ, bool BOTHK, int S, int IDX>
+struct FragSel {
+  static constexpr int sel = !KMAJ ? ((S & 1) * 2 + (IDX & 1)) : (!BOTHK ? (S >> 1) : S);
+  static constexpr int imm = !KMAJ ? ((S >> 1) * 1024 + (IDX >> 1) * 2048) : (!BOTHK ? (IDX * 1024 + (S & 1) * 8) : IDX * 1024);
+};
+template <int IMM>
+__device__ __forceinline__ double lds_f64_imm(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+template <bool KMAJ, bool BOTHK, int S, int IDX, int CNT>
+struct FragLoader {
+  static __device__ __forceinline__ void run(const uint32_t (&r)[4], double* out) {
+    out[IDX] = lds_f64_imm<FragSel<KMAJ, BOTHK, S, IDX>::imm>(r[FragSel<KMAJ, BOTHK, S, IDX>::sel]);
+    FragLoader<KMAJ, BOTHK, S, IDX + 1, CNT>::run(r, out);
+  }
+};
+template <bool KMAJ, bool BOTHK, int S, int CNT>
+struct FragLoader<KMAJ, BOTHK, S, CNT, CNT> {
+  static __device__ __forceinline__ void run(const uint32_t (&)[4], double*) {}
+};
+template <bool KMAJ, bool BOTHK, int S, int CNT>
+__device__ __forceinline__ void load_frags(const uint32_t (&r)[4], double* out) {
+  FragLoader<KMAJ, BOTHK, S, 0, CNT>::run(r, out);
+}
+
 template <bool MS_KMAJ, bool NS_KMAJ>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constant__ CUtensorMap tmapN,
@@ -122,67 +177,81 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constan
   }
   __syncthreads();
 
-  if (warp == GEMM_CONSUMER_WARPS) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      tma_prefetch_desc(&tmapM);
-      tma_prefetch_desc(&tmapN);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
-        TileDesc td = gemm_get_tile(args, tile);
-        for (int k0 = td.k_begin; k0 < td.k_end; k0 += TK) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sN = ring + stage * STAGE_BYTES;
-          uint8_t* sM = sN + NS_TILE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if (NS_KMAJ) {
+  // ===================== TMA producer: thread 0, inline in consumer warp 0 =====================
+  // Four warps per CTA and two CTAs per SM = two warps per SM sub-partition, so each thread may hold the
+  // 64 accumulators + double-buffered fragments without spilling (a fifth, producer-only warp would put three
+  // warps on one sub-partition and cap everyone at 168 registers).  Thread 0 issues the loads of k-stage
+  // c + GSTAGES - 1 just before the CTA consumes k-stage c, i.e. it refills the slot released one iteration ago.
+  const bool is_producer = threadIdx.x == 0;
+  int p_tile = blockIdx.x, p_k0 = 0, p_stage = 0;
+  uint32_t p_phase = 0;
+  bool p_live = false;
+  TileDesc p_td = {0, 0, 0, 0};
+  if (is_producer) {
+    tma_prefetch_desc(&tmapM);
+    tma_prefetch_desc(&tmapN);
+    p_live = p_tile < args.ntiles;
+    if (p_live) {
+      p_td = gemm_get_tile(args, p_tile);
+      p_k0 = p_td.k_begin;
+    }
+  }
+  auto produce_one = [&]() {
+    if (!p_live) return;
+    mbar_wait(&empty_bar[p_stage], p_phase ^ 1);
+    uint8_t* sN = ring + p_stage * STAGE_BYTES;
+    uint8_t* sM = sN + NS_TILE_BYTES;
+    mbar_arrive_expect_tx(&full_bar[p_stage], STAGE_BYTES);
+    if (NS_KMAJ) {
 #pragma unroll
-            for (int b = 0; b < TN / 64; ++b)
-              tma_load_2d(sN + b * 8192, &tmapN, &full_bar[stage], k0, td.c_col + 64 * b);
-          } else {
+      for (int b = 0; b < TN / 64; ++b) tma_load_2d(sN + b * 8192, &tmapN, &full_bar[p_stage], p_k0, p_td.c_col + 64 * b);
+    } else {
 #pragma unroll
-            for (int b = 0; b < TN / 16; ++b)
-              tma_load_2d(sN + b * 2048, &tmapN, &full_bar[stage], td.c_col + 16 * b, k0);
-          }
-          if (MS_KMAJ) {
-            tma_load_2d(sM, &tmapM, &full_bar[stage], k0, td.c_row);
-          } else {
+      for (int b = 0; b < TN / 16; ++b) tma_load_2d(sN + b * 2048, &tmapN, &full_bar[p_stage], p_td.c_col + 16 * b, p_k0);
+    }
+    if (MS_KMAJ) {
+      tma_load_2d(sM, &tmapM, &full_bar[p_stage], p_k0, p_td.c_row);
+    } else {
 #pragma unroll
-            for (int b = 0; b < TM / 16; ++b)
-              tma_load_2d(sM + b * 2048, &tmapM, &full_bar[stage], td.c_row + 16 * b, k0);
-          }
-          if (++stage == GSTAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
+      for (int b = 0; b < TM / 16; ++b) tma_load_2d(sM + b * 2048, &tmapM, &full_bar[p_stage], p_td.c_row + 16 * b, p_k0);
+    }
+    if (++p_stage == GSTAGES) {
+      p_stage = 0;
+      p_phase ^= 1;
+    }
+    p_k0 += TK;
+    if (p_k0 >= p_td.k_end) {
+      p_tile += gridDim.x;
+      p_live = p_tile < args.ntiles;
+      if (p_live) {
+        p_td = gemm_get_tile(args, p_tile);
+        p_k0 = p_td.k_begin;
       }
     }
-    return;
+  };
+  if (is_producer) {
+#pragma unroll 1
+    for (int q = 0; q < GSTAGES - 1; ++q) produce_one();
   }
+  __syncwarp();
 
-  // ===================== DMMA consumers =====================
+  // ===================== DMMA consumers (all four warps) =====================
   const int g = lane >> 2, t = lane & 3;
   const uint32_t ring_u32 = smem_u32(ring);
   int stage = 0;
   uint32_t phase = 0;
 
-  // Per-lane fragment offsets inside a stage, for the 4 k-steps of a stage.
-  // k index used by lane t in k-step s (a permutation of 0..15 chosen so that the
+  // Per-lane fragment addresses.  k index used by lane t in k-step s (a permutation of 0..15 chosen so that the
   // 16 lanes of a half-warp hit 16 distinct 8-byte bank pairs):
   //   any M-major operand present: kk = 2t + (s&1) + 8(s>>1)
   //   both K-major:                kk = 2s + (t&1) + 8(t>>1)
-  uint32_t offN[4][4];  // [kstep][i]
-  uint32_t offM[4][8];  // [kstep][j]
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int kk = (MS_KMAJ && NS_KMAJ) ? (2 * s + (t & 1) + 8 * (t >> 1)) : (2 * t + (s & 1) + 8 * (s >> 1));
-#pragma unroll
-    for (int i = 0; i < 4; ++i) offN[s][i] = tile_off<NS_KMAJ>((warp * 4 + i) * 8 + g, kk);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) offM[s][j] = NS_TILE_BYTES + tile_off<MS_KMAJ>(j * 8 + g, kk);
-  }
+  // Every fragment address is  stage base + one of <= 4 per-lane registers + a compile-time immediate
+  // (FragAddr above), so the main loop is LDS-with-immediate + DMMA only.
+  constexpr bool BOTHK = MS_KMAJ && NS_KMAJ;
+  FragAddr<NS_KMAJ, BOTHK> fN;
+  FragAddr<MS_KMAJ, BOTHK> fM;
+  fN.init(g, t, (uint32_t)(warp * 4096));
+  fM.init(g, t, (uint32_t)NS_TILE_BYTES);
 
   for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
     TileDesc td = gemm_get_tile(args, tile);
@@ -193,19 +262,36 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constan
       for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     for (int k0 = td.k_begin; k0 < td.k_end; k0 += TK) {
+      if (is_producer) produce_one();
+      __syncwarp();
       mbar_wait(&full_bar[stage], phase);
       const uint32_t base = ring_u32 + stage * STAGE_BYTES;
+      uint32_t rn[4], rm[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        rn[q] = base + fN.R[q];
+        rm[q] = base + fM.R[q];
+      }
+      double a[2][4], b[2][8];
+      load_frags<NS_KMAJ, BOTHK, 0, 4>(rn, a[0]);
+      load_frags<MS_KMAJ, BOTHK, 0, 8>(rm, b[0]);
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        double a[4], b[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = lds_f64(base + offN[s][i]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = lds_f64(base + offM[s][j]);
+        // software pipeline: fragments of k-step s+1 are in flight while the 32 DMMAs of k-step s issue
+        if (s == 0) {
+          load_frags<NS_KMAJ, BOTHK, 1, 4>(rn, a[1]);
+          load_frags<MS_KMAJ, BOTHK, 1, 8>(rm, b[1]);
+        } else if (s == 1) {
+          load_frags<NS_KMAJ, BOTHK, 2, 4>(rn, a[0]);
+          load_frags<MS_KMAJ, BOTHK, 2, 8>(rm, b[0]);
+        } else if (s == 2) {
+          load_frags<NS_KMAJ, BOTHK, 3, 4>(rn, a[1]);
+          load_frags<MS_KMAJ, BOTHK, 3, 8>(rm, b[1]);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[s & 1][i], b[s & 1][j]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
