@@ -9,27 +9,54 @@
 //
 // This kernel sits on the critical path of the factorisation (one launch per 128 columns), so it is
 // organised for latency, 512 threads:
-//   for each 32-column sub-panel:
-//     A. one warp factors the 32x32 diagonal sub-block with warp shuffles only (lane = row; the pivot's
-//        1/sqrt comes from one rsqrt + two Newton steps instead of a sqrt and a divide) and inverts it
-//        (lane = column, forward substitution against broadcast shared-memory reads);
-//     B. all threads form the rows below as A21 * inv(L11)^T -- no dependency chain;
-//     C. all threads apply the rank-32 update to the rest of the tile (4x4 register micro-tiles,
-//        lower part only).
+//   for each 32-column sub-panel (c0 = 0, 32, 64, 96):
+//     AB. one thread per row r >= c0 keeps its 32 entries of the sub-panel in registers and runs the 32 column
+//         steps left-looking: v = a[j] - sum_k a[k] L[c0+j, c0+k].  Every thread recomputes the pivot
+//         p = A[jj] - sum_k L[c0+j, c0+k]^2 from the same shared-memory row, so ONE named barrier per column is
+//         enough (the diagonal rows publish their new entry, everybody reads the finished row j at the next
+//         step); 1/sqrt(p) is one rsqrt + two Newton steps instead of a sqrt and a divide.
+//         Meanwhile an otherwise idle warp inverts the previous 32x32 diagonal sub-block (lane = column).
+//     C.  all threads apply the rank-32 update to the rest of the tile (4x4 register micro-tiles, lower part).
 //   The off-diagonal 32x32 blocks of the inverse follow from X_ij = -X_ii sum_k L_ik X_kj, one block
 //   sub-diagonal at a time, as small all-thread products.
-// Shared memory: As[c*128 + r] = A[r, c] (column-major, 128 KB) + the 10 lower 32x32 blocks of the
-// inverse in natural orientation (80 KB); T blocks of the inverse stage live in As's unused upper part.
+// Shared memory: As[c*128 + r] = A[r, c] (column-major, 128 KB) + the 10 lower 32x32 blocks of the inverse in
+// natural orientation (80 KB) + two row-major copies of the current / previous diagonal sub-block (16 KB);
+// T blocks of the inverse stage live in As's unused upper part.
 #pragma once
 #include "common.cuh"
 
 namespace lk {
 
 constexpr int POTF2_THREADS = 512;
-constexpr int POTF2_SMEM_DOUBLES = 128 * 128 + 10 * 1024 + 128 + 8;
+constexpr int POTF2_SMEM_DOUBLES = 128 * 128 + 10 * 1024 + 2 * 1024 + 128 + 128 + 8;
 constexpr int POTF2_SMEM_BYTES = POTF2_SMEM_DOUBLES * 8;
 
 __device__ __forceinline__ int potf2_blk(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+
+__device__ __forceinline__ void potf2_bar(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// inverse of the 32x32 lower-triangular diagonal sub-block kb, by one warp: lane = column c of X.
+// Ld: row-major copy of the sub-block's strict lower part (Ld[i*32 + k] = L[c0+i, c0+k], k < i).
+__device__ __forceinline__ void potf2_invert_diag(const double* __restrict__ Ld, const double* __restrict__ rdiag_c0,
+                                                  double* __restrict__ Xd, int lane) {
+  double x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 1 < i; k += 2) {
+      const double2 l = *reinterpret_cast<const double2*>(Ld + i * 32 + k);
+      s0 = fma(l.x, x[k], s0);
+      s1 = fma(l.y, x[k + 1], s1);
+    }
+    if (i & 1) s0 = fma(Ld[i * 32 + i - 1], x[i - 1], s0);
+    const double rdi = rdiag_c0[i];
+    x[i] = (i == lane) ? rdi : ((i > lane) ? -(s0 + s1) * rdi : 0.0);
+    Xd[lane * 32 + i] = x[i];
+  }
+}
 
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, int jb, double* __restrict__ logdet_blocks,
@@ -37,8 +64,10 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
   extern __shared__ double sm[];
   double* As = sm;                     // 128*128
   double* Xb = sm + 128 * 128;         // 10 blocks of 32x32: Xb[blk][c*32 + r] = X[32i + r, 32j + c]
-  double* rdiag = Xb + 10 * 1024;      // 1 / L_ii
-  double* logp = rdiag + 128;          // 4 partial log sums
+  double* Ldt = Xb + 10 * 1024;        // 2 x (32x32) row-major diagonal sub-blocks (double buffered)
+  double* rdiag = Ldt + 2 * 1024;      // 1 / L_ii
+  double* diag = rdiag + 128;          // L_ii
+  double* logp = diag + 128;           // 4 partial log sums
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   double* Ablk = A + (long long)jb * ld + jb;
@@ -52,82 +81,57 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
   bool ok = true;
   for (int kb = 0; kb < 4; ++kb) {
     const int c0 = 32 * kb;
-    // ---------------- A: diagonal 32x32 sub-block, one warp ----------------
-    if (warp == 0) {
+    const int nrow = 128 - c0;
+    double* Ld = Ldt + (kb & 1) * 1024;
+    if (tid < nrow) {
+      // ---------------- AB: 32 column steps, one thread per row ----------------
+      const int row = c0 + tid;
       double a[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = As[(c0 + j) * 128 + c0 + lane];
-      double logsum = 0.0, rd_self = 0.0;
+      for (int j = 0; j < 32; ++j) a[j] = As[(c0 + j) * 128 + row];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const double piv = __shfl_sync(0xffffffffu, a[j], j);
+        potf2_bar(nrow);  // row j of Ld is complete (entries k < j)
+        double v0 = a[j], v1 = 0.0;
+        double p0 = As[(c0 + j) * 128 + c0 + j], p1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < j; k += 2) {
+          const double2 l = *reinterpret_cast<const double2*>(Ld + j * 32 + k);
+          v0 = fma(-a[k], l.x, v0);
+          v1 = fma(-a[k + 1], l.y, v1);
+          p0 = fma(-l.x, l.x, p0);
+          p1 = fma(-l.y, l.y, p1);
+        }
+        if (j & 1) {
+          const double l = Ld[j * 32 + j - 1];
+          v0 = fma(-a[j - 1], l, v0);
+          p0 = fma(-l, l, p0);
+        }
+        const double piv = p0 + p1;
         ok = ok && (piv > 0.0);
         double rd = rsqrt(piv);
         double dj = piv * rd;
         dj = fma(fma(-dj, dj, piv) * 0.5, rd, dj);  // Newton step: dj = sqrt(piv) to working accuracy
         rd = fma(fma(-dj, rd, 1.0), rd, rd);        // rd = 1 / dj
-        a[j] = (lane == j) ? dj : a[j] * rd;
-        if (lane == j) {
-          logsum = log(dj);
-          rd_self = rd;
-        }
-#pragma unroll
-        for (int j2 = j + 1; j2 < 32; ++j2) {
-          const double l2 = __shfl_sync(0xffffffffu, a[j], j2);  // L[c0+j2, c0+j]
-          a[j2] -= a[j] * l2;
+        a[j] = (tid == j) ? dj : (v0 + v1) * rd;
+        if (tid > j && tid < 32) Ld[tid * 32 + j] = a[j];
+        if (tid == j) {
+          diag[c0 + j] = dj;
+          rdiag[c0 + j] = rd;
         }
       }
+      potf2_bar(nrow);  // everybody is done reading the original diagonal entries from As
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j <= lane) As[(c0 + j) * 128 + c0 + lane] = a[j];
-      rdiag[c0 + lane] = rd_self;
-      const double ls = warp_sum(logsum);
-      if (lane == 0) logp[kb] = ls;
-      __syncwarp();
-      // inverse of the sub-block: lane = column c of X, x[i] = X[i, c]
-      double x[32];
-      double* Xd = Xb + potf2_blk(kb, kb) * 1024;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k) s = fma(As[(c0 + k) * 128 + c0 + i], x[k], s);
-        const double rdi = rdiag[c0 + i];
-        x[i] = (i == lane) ? rdi : ((i > lane) ? -s * rdi : 0.0);
-        Xd[lane * 32 + i] = x[i];
-      }
+        if (tid >= j) As[(c0 + j) * 128 + row] = a[j];
+    } else if (warp == 4 && kb > 0) {
+      // inverse of the previous diagonal sub-block, off the critical chain
+      potf2_invert_diag(Ldt + ((kb - 1) & 1) * 1024, rdiag + c0 - 32, Xb + potf2_blk(kb - 1, kb - 1) * 1024, lane);
     }
     __syncthreads();
     const int R0 = c0 + 32;
     const int m = 128 - R0;  // rows / columns left after this sub-panel
     if (m > 0) {
-      // ---------------- B: L21 = A21 * inv(L11)^T ----------------
-      {
-        const int rl = tid & 127, part = tid >> 7;  // row, group of 8 output columns
-        const bool act = rl < m;
-        double in[32], out[8];
-        if (act) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) in[k] = As[(c0 + k) * 128 + R0 + rl];
-          const double* Xd = Xb + potf2_blk(kb, kb) * 1024;
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              // L21[r, j] = sum_{k <= j} A21[r, k] X[j, k] ; X[j, k] = Xd[k*32 + j], zero above the diagonal
-              s = fma(in[k], Xd[k * 32 + part * 8 + jj], s);
-            }
-            out[jj] = s;
-          }
-        }
-        __syncthreads();
-        if (act) {
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) As[(c0 + part * 8 + jj) * 128 + R0 + rl] = out[jj];
-        }
-      }
-      __syncthreads();
       // ---------------- C: rank-32 update of the remaining lower part ----------------
       const int mq = m >> 2;
       for (int mt = tid; mt < mq * mq; mt += POTF2_THREADS) {
@@ -163,11 +167,15 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
     }
   }
 
-  // failure flag (NaN-safe: piv > 0 is false for NaN) and the block's log-determinant part
-  if (warp == 0 && lane == 0) {
-    if (!ok) atomicExch(info, 1);
-    logdet_blocks[blk_index] = ((logp[0] + logp[1]) + logp[2]) + logp[3];
+  // failure flag (NaN-safe: piv > 0 is false for NaN; every thread of rows 0..127 saw every pivot) and the block's
+  // log-determinant part, summed in a fixed order
+  if (tid < 128) {
+    const double ls = warp_sum(log(diag[tid]));
+    if (lane == 0) logp[warp] = ls;
   }
+  if (tid == 0 && !ok) atomicExch(info, 1);  // thread 0 took part in all four sub-panels
+  __syncthreads();
+  if (tid == 0) logdet_blocks[blk_index] = ((logp[0] + logp[1]) + logp[2]) + logp[3];
 
   // write L back (lower part incl. diagonal; strict upper zero)
   for (int idx = tid; idx < 128 * 64; idx += POTF2_THREADS) {
@@ -182,6 +190,8 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
   // T_ij = sum_{k=j}^{i-1} L_ik X_kj  is parked in As's upper block (j, i);  X_ij = -X_ii T_ij.
   for (int dd = 1; dd < 4; ++dd) {
     const int nblk = 4 - dd;
+    // the last diagonal sub-block's inverse is not needed by the T products of the first sub-diagonal
+    if (dd == 1 && warp == 15) potf2_invert_diag(Ldt + 1024, rdiag + 96, Xb + potf2_blk(3, 3) * 1024, lane);
     for (int e = tid; e < nblk * 1024; e += POTF2_THREADS) {
       const int b = e >> 10, rr = e & 31, cc = (e >> 5) & 31;
       const int j = b, i = b + dd;
