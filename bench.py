@@ -234,13 +234,12 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from libkriging_b200 import _capi
+    from libkriging_b200.kriging import Kriging
     comm = None
     if world > 1:
         from libkriging_b200 import parallel
         comm = parallel.init_from_env("nccl")
-
-    from libkriging_b200 import _capi
-    from libkriging_b200.kriging import Kriging
 
     def barrier():
         if world > 1:
@@ -264,6 +263,16 @@ def run_b200_arm(args):
     n, d, K, W = args.n, args.d, args.steps, max(args.warmup, 3)
     X, y = synth(n, d, 123)
     F = np.ones((n, 1))
+    if not args.smooth_y:
+        # y = one draw of the GP itself at theta* = 0.5 ("a draw from the GP itself at a known theta*"):
+        # y = L z with L = chol(R(theta*)) taken from the engine (untimed set-up), so that the fit has an interior,
+        # well-conditioned optimum instead of running into the theta upper bound.
+        with _capi.Engine(X, y, F, kernel=KERNEL, device=local) as e0:
+            e0.objective("LL", np.full(d, 0.5), False)
+            L = e0.export("L")
+        z = np.random.Generator(np.random.PCG64(321)).standard_normal(n)
+        y = 1.5 + 2.0 * (L @ z)
+        del L
     # pinned host staging for the e2e leg (column-major X)
     Xp = torch.from_numpy(np.ascontiguousarray(X.T)).pin_memory()
     yp = torch.from_numpy(y.copy()).pin_memory()
@@ -398,6 +407,7 @@ def run_b200_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n, d), "n": n, "d": d, "kernel": KERNEL, "objective": "LL", "regmodel": "constant",
+                   "y": "analytic smooth function" if args.smooth_y else "GP draw at theta*=0.5 (y = 1.5 + 2 L z, seed 321)",
                    "l2": "inputs larger than L2 (each n x n fp64 buffer is %.1f GB)" % (8.0 * n * n / 1e9),
                    "parallelism": f"multistart x{world}: one independent evaluation stream per GPU, no data-path collective"},
         "clocks": clocks,
@@ -427,6 +437,7 @@ def main():
     ap.add_argument("--d", type=int, default=10)
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--smooth-y", action="store_true", help="analytic y instead of the GP draw (debug)")
     ap.add_argument("--peak", default="cublas", choices=["cublas", "max"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -811,45 +811,46 @@ struct Engine {
     double rc2 = 0.0;
     float ms_cov = 0, ms_chol = 0, ms_rcond = 0, ms_trtri = 0;
     while (true) {
+      have_W = false;
       CUDA_CHECK(cudaEventRecord(ev_t[1], s_main));
       cov_build(A, alpha, inv_sigma2, diag_add, s_main);
       CUDA_CHECK(cudaEventRecord(ev_t[2], s_main));
       cholesky();
       CUDA_CHECK(cudaEventRecord(ev_t[3], s_main));
-      if (need_inverse) trtri();
-      CUDA_CHECK(cudaEventRecord(ev_t[4], s_main));
-      // info + norms
+      // info + ||L||_1 : a failed factorisation goes straight to the next rung of the ladder
       launches += 2;
       tri_colsum_abs_kernel<<<(n * 32 + 255) / 256, 256, 0, s_main>>>(A, ld, n, dcolsum);
       vec_max_kernel<<<1, 256, 0, s_main>>>(dcolsum, n, dscal + SC_NORML);
-      if (need_inverse) {
-        launches += 2;
-        tri_colsum_abs_kernel<<<(n * 32 + 255) / 256, 256, 0, s_main>>>(W, ld, n, dcolsum);
-        vec_max_kernel<<<1, 256, 0, s_main>>>(dcolsum, n, dscal + SC_NORMW);
-      }
-      CUDA_CHECK(cudaMemcpyAsync(hpin, dscal + SC_NORML, 16, cudaMemcpyDeviceToHost, s_main));
+      CUDA_CHECK(cudaMemcpyAsync(hpin, dscal + SC_NORML, 8, cudaMemcpyDeviceToHost, s_main));
       CUDA_CHECK(cudaMemcpyAsync(hpin + 2, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s_main));
       CUDA_CHECK(cudaStreamSynchronize(s_main));
       float t;
       cudaEventElapsedTime(&t, ev_t[1], ev_t[2]); ms_cov += t;
       cudaEventElapsedTime(&t, ev_t[2], ev_t[3]); ms_chol += t;
-      cudaEventElapsedTime(&t, ev_t[3], ev_t[4]); ms_trtri += t;
-      const double normL = hpin[0], normW = hpin[1];
+      const double normL = hpin[0];
       int info;
       memcpy(&info, hpin + 2, sizeof(int));
-      bool ok = (info == 0) && std::isfinite(normL);
+      const bool ok = (info == 0) && std::isfinite(normL);
       bool wrong_rcond = rcond_check;
       if (ok && rcond_check) {
-        CUDA_CHECK(cudaEventRecord(ev_t[5], s_main));
-        double rc;
-        if (need_inverse && std::isfinite(normW) && normW > 0.0) {
-          // exact 1-norm of L^-1 is available: dtrcon's estimate can only be larger than this rcond,
-          // so accepting here is exactly the reference's decision; fall back to the estimator otherwise.
-          rc = (1.0 / normL) / normW;
-          if (rc * rc < min_rcond) rc = rcond_estimate(normL);
-        } else {
-          rc = rcond_estimate(normL);
+        double rc = -1.0;
+        if (need_inverse && inc == 0) {
+          // first rung, gradient path: L^-1 is needed anyway, and its exact 1-norm is a lower bound of what dtrcon
+          // estimates, so accepting on it is exactly the reference's decision; otherwise the estimator decides.
+          CUDA_CHECK(cudaEventRecord(ev_t[3], s_main));
+          trtri();
+          CUDA_CHECK(cudaEventRecord(ev_t[4], s_main));
+          launches += 2;
+          tri_colsum_abs_kernel<<<(n * 32 + 255) / 256, 256, 0, s_main>>>(W, ld, n, dcolsum);
+          vec_max_kernel<<<1, 256, 0, s_main>>>(dcolsum, n, dscal + SC_NORMW);
+          CUDA_CHECK(cudaMemcpyAsync(hpin, dscal + SC_NORMW, 8, cudaMemcpyDeviceToHost, s_main));
+          CUDA_CHECK(cudaStreamSynchronize(s_main));
+          cudaEventElapsedTime(&t, ev_t[3], ev_t[4]); ms_trtri += t;
+          const double normW = hpin[0];
+          if (std::isfinite(normW) && normW > 0.0) rc = (1.0 / normL) / normW;
         }
+        CUDA_CHECK(cudaEventRecord(ev_t[5], s_main));
+        if (!(rc * rc >= min_rcond) || rc < 0.0) rc = rcond_estimate(normL);  // dtrcon restated (Higham / Hager)
         rc2 = rc * rc;
         wrong_rcond = rc2 < min_rcond;
         CUDA_CHECK(cudaEventRecord(ev_t[6], s_main));
@@ -869,6 +870,15 @@ struct Engine {
         continue;
       }
       break;
+    }
+    if (need_inverse && !have_W) {
+      // accepted on a later rung: L^-1 is formed once, after the ladder
+      CUDA_CHECK(cudaEventRecord(ev_t[3], s_main));
+      trtri();
+      CUDA_CHECK(cudaEventRecord(ev_t[4], s_main));
+      CUDA_CHECK(cudaStreamSynchronize(s_main));
+      float t;
+      cudaEventElapsedTime(&t, ev_t[3], ev_t[4]); ms_trtri += t;
     }
     last_diag_add = diag_add;
     out->n_jitter = inc;

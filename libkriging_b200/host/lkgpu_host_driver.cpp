@@ -1,0 +1,106 @@
+// lkgpu_host_driver.cpp -- command-line front end of the C++ host (lkgpu::Kriging), same work-directory protocol
+// and JSON output as oracle/ref_driver.cpp so that the tests can put the two side by side:
+//   <workdir>/cfg.txt (key=value), X.bin (n*d column-major), y.bin, noise.bin, theta.bin (nt*d), gamma.bin, Xn.bin (m*d)
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+
+#include "lkgpu_kriging.hpp"
+
+static std::vector<double> read_bin(const std::string& path, size_t count) {
+  std::vector<double> v(count);
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", path.c_str()); exit(2); }
+  const size_t got = fread(v.data(), sizeof(double), count, f);
+  fclose(f);
+  if (got != count) { fprintf(stderr, "short read %s\n", path.c_str()); exit(2); }
+  return v;
+}
+static bool exists(const std::string& p) { std::ifstream f(p); return f.good(); }
+static void jvec(std::ostream& os, const char* key, const arma::vec& v) {
+  os << "\"" << key << "\": [";
+  os.precision(17);
+  for (arma::uword i = 0; i < v.n_elem; i++) os << (i ? ", " : "") << std::scientific << v[i];
+  os << "]";
+}
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: lkgpu_host_driver <workdir>\n"); return 2; }
+  const std::string wd = argv[1];
+  std::map<std::string, std::string> cfg;
+  {
+    std::ifstream f(wd + "/cfg.txt");
+    std::string line;
+    while (std::getline(f, line)) {
+      auto eq = line.find('=');
+      if (eq != std::string::npos) cfg[line.substr(0, eq)] = line.substr(eq + 1);
+    }
+  }
+  auto gets = [&](const char* k, const char* def) { return cfg.count(k) ? cfg[k] : std::string(def); };
+  auto geti = [&](const char* k, int def) { return cfg.count(k) ? atoi(cfg[k].c_str()) : def; };
+  auto getd = [&](const char* k, double def) { return cfg.count(k) ? atof(cfg[k].c_str()) : def; };
+  const int n = geti("n", 0), d = geti("d", 0);
+  const std::string mode = gets("mode", "eval"), kernel = gets("kernel", "gauss"), noise_model = gets("noise_model", "none");
+  const std::string objective = gets("objective", "LL"), regmodel = gets("regmodel", "constant"), optim = gets("optim", "none");
+  const bool normalize = geti("normalize", 0) != 0;
+  const int nt = geti("ntheta", 1), want_grad = geti("grad", 1), device = geti("device", 0);
+  try {
+    arma::mat X(read_bin(wd + "/X.bin", (size_t)n * d).data(), n, d);
+    arma::vec y(read_bin(wd + "/y.bin", n).data(), n);
+    arma::vec noise;
+    if (noise_model == "hetero") noise = arma::vec(read_bin(wd + "/noise.bin", n).data(), n);
+    using NM = lkgpu::Kriging::NoiseModel;
+    const NM nm = noise_model == "nugget" ? NM::Nugget : noise_model == "hetero" ? NM::Heterogeneous : NM::None;
+    lkgpu::Kriging k(kernel, nm, device);
+    lkgpu::Kriging::Parameters prm;
+    if (exists(wd + "/theta.bin")) prm.theta = arma::mat(read_bin(wd + "/theta.bin", (size_t)nt * d).data(), nt, d);
+    if (cfg.count("sigma2")) { prm.sigma2 = getd("sigma2", 1.0); prm.is_sigma2_estim = geti("est_sigma2", 0) != 0; }
+    if (cfg.count("nugget")) { prm.nugget = getd("nugget", 0.0); prm.is_nugget_estim = geti("est_nugget", 0) != 0; }
+    std::ostringstream js;
+    js << "{";
+    const double t0 = now_s();
+    if (nm == NM::Heterogeneous) k.fit(y, noise, X, regmodel, normalize, mode == "fit" ? optim : "none", objective, prm);
+    else k.fit(y, X, regmodel, normalize, mode == "fit" ? optim : "none", objective, prm);
+    js << "\"fit_s\": " << (now_s() - t0) << ", \"n_eval\": " << k.n_eval() << ", ";
+    if (mode == "eval") {
+      const int gd = d + (nm == NM::None ? 0 : 1);
+      arma::vec gamma = exists(wd + "/gamma.bin") ? arma::vec(read_bin(wd + "/gamma.bin", gd).data(), gd)
+                                                   : arma::vec(prm.theta.value().row(0).t());
+      std::tuple<double, arma::vec> res;
+      if (objective == "LL") res = k.logLikelihoodFun(gamma, want_grad != 0);
+      else if (objective == "LOO") res = k.leaveOneOutFun(gamma, want_grad != 0);
+      else res = k.logMargPostFun(gamma, want_grad != 0);
+      js.precision(17);
+      js << "\"value\": " << std::scientific << std::get<0>(res) << ", ";
+      jvec(js, "grad", std::get<1>(res)); js << ", ";
+    }
+    js.precision(17);
+    jvec(js, "theta", k.theta()); js << ", ";
+    jvec(js, "beta", k.beta()); js << ", ";
+    js << "\"sigma2\": " << std::scientific << k.sigma2() << ", \"nugget\": " << k.nugget() << ", ";
+    if (mode == "fit") {
+      const double ll = objective == "LOO" ? k.leaveOneOut() : (objective == "LMP" ? k.logMargPost() : k.logLikelihood());
+      js << "\"objective_at_fit\": " << ll << ", ";
+    }
+    if (exists(wd + "/Xn.bin")) {
+      const int m = geti("m", 0);
+      arma::mat Xn(read_bin(wd + "/Xn.bin", (size_t)m * d).data(), m, d);
+      auto pr = k.predict(Xn, true);
+      jvec(js, "pred_mean", std::get<0>(pr)); js << ", ";
+      jvec(js, "pred_sd", std::get<1>(pr)); js << ", ";
+    }
+    js << "\"n\": " << n << ", \"d\": " << d << "}";
+    std::cout << js.str() << std::endl;
+  } catch (const std::exception& e) {
+    std::cout << "{\"error\": \"" << e.what() << "\"}" << std::endl;
+    return 1;
+  }
+  return 0;
+}

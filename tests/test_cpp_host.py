@@ -1,0 +1,75 @@
+"""The C++ host (libkriging_b200/host: lkgpu::Kriging with the Armadillo-facing API and the lbfgsb_cpp loop of the
+reference's host, objective evaluations on the GPU through liblkgpu.so).
+CPU part: the driver is built and fails loudly without a GPU.  GPU part (-m gpu): its fits against fits of the
+unmodified reference, same fixtures and gates as tests/test_gpu_fit.py -- here the L-BFGS-B iterates come from the
+very Lbfgsb.3.0 code the reference runs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from libkriging_b200 import host
+from tests.util import GOLDEN, load_refgen, relerr, relerr_vec, synth
+
+GEN = load_refgen()
+with open(os.path.join(GOLDEN, "refgen_fits_wc.json")) as _f:
+    WC = json.load(_f)["fits"]
+
+
+def test_host_driver_built_and_fails_loudly_without_gpu():
+    import torch
+    assert host.build(), "libkriging_b200/host/_build/lkgpu_host_driver missing (build_host.sh)"
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    X, y, _ = synth(20, 2, 1)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        host.run(X, y, kernel="gauss", mode="fit", optim="BFGS")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", WC, ids=[c["name"] for c in WC])
+def test_cpp_host_fit_well_conditioned_path(c):
+    X, y, _ = synth(c["n"], c["d"], c["seed"], "smooth")
+    rng = np.random.Generator(np.random.PCG64(c["seed"] + 1000))
+    Xn = rng.random((25, c["d"]))
+    r = host.run(X, y, kernel=c["kernel"], noise_model=c["noise_model"], objective=c["objective"], mode="fit",
+                 optim="BFGS", theta=np.full((1, c["d"]), c["theta0"]), Xn=Xn)
+    tol = 1e-6 if c["path_min_rcond2"] >= 1e-12 else 1e-4
+    assert relerr(r["theta"], c["theta"]) < tol
+    assert relerr(r["sigma2"], c["sigma2"]) < 10 * tol
+    if c["noise_model"] == "nugget":
+        assert relerr(r["nugget"], c["nugget"]) < 100 * tol
+    assert relerr_vec(r["beta"], c["beta"]) < 10 * tol
+    assert relerr(r["objective_at_fit"], c["objective_at_fit"]) < 1e-6
+    assert relerr_vec(r["pred_mean"], c["pred_mean"]) < 10 * tol
+    assert relerr_vec(r["pred_sd"], c["pred_sd"]) < 100 * tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", GEN["fits"], ids=[c["name"] for c in GEN["fits"]])
+def test_cpp_host_fit_default_starts(c):
+    """Default random starts (see tests/test_gpu_fit.py for why theta is gated at the optimiser's tolerance here)."""
+    X, y, noise = synth(c["n"], c["d"], c["seed"], c.get("yfun", "prodsin"))
+    r = host.run(X, y, kernel=c["kernel"], noise_model=c["noise_model"], objective=c["objective"], mode="fit",
+                 optim=c["optim"], regmodel=c.get("regmodel", "constant"), normalize=c.get("normalize", False),
+                 noise=noise if c["noise_model"] == "hetero" else None)
+    if c["objective"] == "LOO":
+        assert r["objective_at_fit"] <= c["objective_at_fit"] * (1 + 1e-3)
+    else:
+        assert relerr(r["objective_at_fit"], c["objective_at_fit"]) < 1e-6
+        assert relerr(r["theta"], c["theta"]) < 5e-3
+        assert relerr(r["sigma2"], c["sigma2"]) < 5e-2
+
+
+@pytest.mark.gpu
+def test_cpp_host_objective_matches_ctypes_path():
+    """Same engine behind both hosts: lkgpu::Kriging::logLikelihoodFun == _capi.Engine.objective bit for bit."""
+    from libkriging_b200 import _capi
+    X, y, _ = synth(300, 4, 9, "smooth")
+    th = np.full(4, 0.5)
+    r = host.run(X, y, kernel="matern5_2", objective="LL", mode="eval", theta=th[None, :], grad=True)
+    with _capi.Engine(X, y, np.ones((300, 1)), kernel="matern5_2") as e:
+        v, g = e.objective("LL", th, True)
+    assert r["value"] == v
+    assert np.array_equal(np.array(r["grad"]), g)
