@@ -149,6 +149,11 @@ void* lkgpu_get_stream(void* handle);
  * returns TFLOP/s in *tflops.  Used by bench.py for the roofline denominator. */
 int lkgpu_probe_fp64_peak(int device, int mode, double* tflops);
 
+/* Free / total bytes of device memory: the host sizes the number of concurrent handles (one per
+ * multistart row in flight, BASELINE cfg 5) with it.  The reference preallocates one KModel per start
+ * (src/lib/Kriging.cpp:1861-1874) without such a check. */
+int lkgpu_mem_info(int device, unsigned long long* free_bytes, unsigned long long* total_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,7 @@ def lib():
     L.lkgpu_get_stream.argtypes = [vp]
     L.lkgpu_get_stream.restype = C.c_void_p
     L.lkgpu_probe_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
+    L.lkgpu_mem_info.argtypes = [C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     _lib = L
     return L
 
@@ -91,6 +92,13 @@ def probe_fp64_peak(device=0, mode=0) -> float:
     return v.value
 
 
+def mem_info(device=0):
+    """(free, total) bytes of device memory."""
+    f, t = C.c_ulonglong(0), C.c_ulonglong(0)
+    _check(lib().lkgpu_mem_info(device, C.byref(f), C.byref(t)))
+    return f.value, t.value
+
+
 class Engine:
     """One lkgpu handle = the device-resident KModel workspace of one (process, start)."""
 
@@ -100,7 +108,7 @@ class Engine:
         F = np.asfortranarray(np.asarray(F, dtype=np.float64).reshape(X.shape[0], -1))
         self.n, self.d = X.shape
         self.p = F.shape[1]
-        self.kernel, self.noise_model = kernel, noise_model
+        self.kernel, self.noise_model, self.device = kernel, noise_model, device
         nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64).ravel()
         self._h = C.c_void_p()
         _check(lib().lkgpu_create(C.byref(self._h), device, self.n, self.d, self.p, _ptr(X), _ptr(y), _ptr(F), _ptr(nz),

@@ -213,6 +213,7 @@ struct Engine {
   // state of the last evaluation
   bool have_model = false, have_W = false, have_V = false, have_x = false;
   double last_alpha = 1.0, last_inv_sigma2 = 0.0, last_diag_add = 0.0;
+  int last_n_jitter = 0;
   std::vector<double> last_theta;
 
   ~Engine() { release(); }
@@ -834,9 +835,12 @@ struct Engine {
       bool wrong_rcond = rcond_check;
       if (ok && rcond_check) {
         double rc = -1.0;
-        if (need_inverse && inc == 0) {
+        if (need_inverse && inc == 0 && last_n_jitter == 0) {
           // first rung, gradient path: L^-1 is needed anyway, and its exact 1-norm is a lower bound of what dtrcon
           // estimates, so accepting on it is exactly the reference's decision; otherwise the estimator decides.
+          // (When the previous evaluation on this handle climbed the ladder, the optimiser is in the numerically
+          // singular region and this rung is likely to be rejected: the O(n^2) estimator goes first and L^-1 is
+          // formed once, after the ladder -- same decisions, one TRTRI less per evaluation.)
           CUDA_CHECK(cudaEventRecord(ev_t[3], s_main));
           trtri();
           CUDA_CHECK(cudaEventRecord(ev_t[4], s_main));
@@ -881,6 +885,7 @@ struct Engine {
       cudaEventElapsedTime(&t, ev_t[3], ev_t[4]); ms_trtri += t;
     }
     last_diag_add = diag_add;
+    last_n_jitter = inc;
     out->n_jitter = inc;
     out->rcond = rc2;
     out->info = 0;
@@ -1212,6 +1217,19 @@ void lkgpu_destroy(void* handle) {
 void* lkgpu_get_stream(void* handle) { return handle ? (void*)static_cast<Engine*>(handle)->s_main : nullptr; }
 
 long long lkgpu_launch_count(void* handle) { return handle ? static_cast<Engine*>(handle)->launches : 0; }
+
+int lkgpu_mem_info(int device, unsigned long long* free_bytes, unsigned long long* total_bytes) {
+  LK_TRY
+  if (!free_bytes || !total_bytes) throw LkError{"null argument"};
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw LkError{"lkgpu: no CUDA device available"};
+  CUDA_CHECK(cudaSetDevice(device));
+  size_t f = 0, t = 0;
+  CUDA_CHECK(cudaMemGetInfo(&f, &t));
+  *free_bytes = f;
+  *total_bytes = t;
+  LK_CATCH
+}
 
 int lkgpu_probe_fp64_peak(int device, int mode, double* tflops) {
   LK_TRY

@@ -62,6 +62,12 @@ class GpuBackend:
     def export(self, which):
         return self.engine.export(which)
 
+    def max_handles(self):
+        """How many handles of this size fit in 70 % of the device memory that is free now (+ this one)."""
+        free, _ = self._capi.mem_info(self.engine.device)
+        N = (self.engine.n + 127) // 128 * 128
+        return 1 + int(0.7 * free // (3 * 8 * N * N + (64 << 20)))
+
     def predict(self, Xn, Fn, beta, r_on_factor):
         return self.engine.predict(Xn, Fn, beta, r_on_factor)
 
@@ -138,7 +144,8 @@ class Kriging:
     """Kriging(kernel, noise_model="none").  NuggetKriging == noise_model="nugget",
     NoiseKriging == noise_model="hetero" (reference Kriging.hpp:45-49)."""
 
-    def __init__(self, kernel: str, noise_model: str = "none", *, device: int | None = None, backend_factory=None):
+    def __init__(self, kernel: str, noise_model: str = "none", *, device: int | None = None, backend_factory=None,
+                 concurrent_starts: int | None = None):
         if kernel not in ("gauss", "exp", "matern3_2", "matern5_2"):
             raise ValueError(f"Unsupported covariance kernel: {kernel}")
         nm = _NOISE_ALIASES.get(noise_model.lower())
@@ -149,6 +156,7 @@ class Kriging:
         self._device = device
         self._backend_factory = backend_factory or _default_backend_factory
         self._backend = None
+        self._concurrent_starts = concurrent_starts
         self.config = _optim.OptimConfig.from_env()
         self.m_is_empty = True
         self.fit_log = {}
@@ -350,7 +358,7 @@ class Kriging:
 
         sign = 1.0 if objective == "LOO" else -1.0
 
-        def fit_ofn(gamma, want_grad):
+        def fit_ofn(gamma, want_grad, be=be):
             v = rp.frm(gamma)
             val, grad = be.objective(objective, v, want_grad)
             if want_grad:
@@ -365,7 +373,7 @@ class Kriging:
             factr = cfg.objective_rel_tolerance / 1e-13
 
         # ---- one L-BFGS-B run per start (optimize_worker, Kriging.cpp:1904-2084) ----
-        def optimize_worker(start_idx):
+        def optimize_worker(start_idx, be=be):
             res = dict(start_index=start_idx, objective_value=math.inf, success=False, n_eval=0)
             try:
                 theta_start = theta0[start_idx % multistart].copy()
@@ -381,7 +389,7 @@ class Kriging:
 
                 def fg(x):
                     counter[0] += 1
-                    return fit_ofn(x, True)
+                    return fit_ofn(x, True, be)
 
                 while retry <= cfg.max_restart:
                     r = lbfgsb_minimize(fg, gamma_tmp, lo_loc, up_loc, max_iter=cfg.max_iteration, pgtol=pgtol,
@@ -402,7 +410,7 @@ class Kriging:
                         retry += 1
                     else:
                         break
-                val, _ = fit_ofn(best_gamma, False)  # final evaluation (Kriging.cpp:2044)
+                val, _ = fit_ofn(best_gamma, False, be)  # final evaluation (Kriging.cpp:2044)
                 counter[0] += 1
                 res.update(objective_value=val, gamma=best_gamma, success=True, n_eval=counter[0], retries=retry)
             except Exception as e:  # one failed start must not kill the fit (Kriging.cpp:2075-2081)
@@ -410,7 +418,40 @@ class Kriging:
             return res
 
         my_starts = list(range(multistart)) if comm is None else comm.my_starts(multistart)
-        results = {s: optimize_worker(s) for s in my_starts}
+        ncon = self._concurrency(len(my_starts), n)
+        if ncon <= 1:
+            results = {s: optimize_worker(s) for s in my_starts}
+        else:
+            # Batched-occupancy path (BASELINE cfg 5, SURVEY.md §8b "several handles per device on separate
+            # streams"): a mid-size factorisation cannot fill 148 SMs (its panel chain is latency-bound), so this
+            # rank's starts run concurrently, one engine handle (own workspaces, own streams) and one host thread
+            # each.  Evaluations are deterministic (fixed-order reductions), so every start's trajectory is
+            # bitwise the one the sequential loop produces; the argmin below is still taken in start order.
+            import queue
+            from concurrent.futures import ThreadPoolExecutor
+            pool_be = queue.SimpleQueue()
+            pool_be.put(be)
+            extra_be = []
+            for _ in range(ncon - 1):
+                b = self._backend_factory(self.m_X, self.m_y, self.m_F, self.m_kernel, self.m_noise_model,
+                                          self.m_noise, dev)
+                b.set_params(self.m_est_sigma2, self.m_sigma2, self.m_est_nugget, self.m_nugget, self.m_alpha)
+                extra_be.append(b)
+                pool_be.put(b)
+
+            def run_start(s):
+                b = pool_be.get()
+                try:
+                    return optimize_worker(s, b)
+                finally:
+                    pool_be.put(b)
+
+            try:
+                with ThreadPoolExecutor(max_workers=ncon) as ex:
+                    results = dict(zip(my_starts, ex.map(run_start, my_starts)))
+            finally:
+                for b in extra_be:
+                    b.close()
 
         # ---- argmin over successful starts, strict '<' in start order (Kriging.cpp:2097-2114) ----
         if comm is None:
@@ -465,6 +506,21 @@ class Kriging:
         return self
 
     # ---- helpers ----
+    def _concurrency(self, n_starts, n):
+        """Number of engine handles this process runs concurrently for its multistart rows.  Explicit:
+        Kriging(..., concurrent_starts=K) or LKGPU_CONCURRENT_STARTS; automatic: up to 8 for n <= 8192 (a
+        factorisation that size leaves most SMs idle), 1 above, limited by free device memory."""
+        import os
+        want = self._concurrent_starts
+        if want is None and os.environ.get("LKGPU_CONCURRENT_STARTS"):
+            want = int(os.environ["LKGPU_CONCURRENT_STARTS"])
+        if want is None:
+            want = 8 if n <= 8192 else 1
+        want = max(1, min(int(want), n_starts))
+        if want > 1 and hasattr(self._backend, "max_handles"):
+            want = max(1, min(want, self._backend.max_handles()))
+        return want
+
     def _push_params(self):
         self._backend.set_params(self.m_est_sigma2, self.m_sigma2, getattr(self, "m_est_nugget", True), self.m_nugget,
                                  self.m_alpha)

@@ -1,0 +1,124 @@
+"""GPU parity at the full shapes of BASELINE.json configs 3, 4 and 5 (config 2 is in test_gpu_parity.py), through
+the C ABI.  Where the oracle finishes in seconds it is the checker; above that, size-independent properties of the
+domain: L L^T v = R v (pins the Cholesky factor and hence the log-determinant), R x = y - F beta (pins the solves),
+the leave-one-out errors against their definition (refit without point i), analytic gradients against central
+differences of the objective, and bitwise equality of the concurrent multistart path with the sequential one."""
+import numpy as np
+import pytest
+
+from oracle import kriging_oracle as ko
+from tests.util import relerr, relerr_vec, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from libkriging_b200 import _capi
+    return _capi
+
+
+def _rows_of_R(X, rows, theta, kernel, alpha=1.0):
+    """Rows `rows` of the reference's R (off-diagonal alpha * rho, diagonal 1), from the oracle's kernel."""
+    dx = X[rows, None, :] - X[None, :, :]
+    R = alpha * ko.corr_from_dx(dx, theta, kernel)
+    R[np.arange(len(rows)), rows] = 1.0
+    return R
+
+
+def _fd_check(e, obj, gamma, g, rng, h, tol):
+    u = rng.standard_normal(gamma.size)
+    u /= np.linalg.norm(u)
+    vp, _ = e.objective(obj, gamma + h * u, want_grad=False)
+    vm, _ = e.objective(obj, gamma - h * u, want_grad=False)
+    fd = (vp - vm) / (2 * h)
+    assert abs(fd - g @ u) / abs(fd) < tol, (fd, g @ u)
+
+
+def test_cfg4_nugget_matern32_n40000(capi):
+    """BASELINE config 4 shape: NuggetKriging('matern3_2') LL + gradient at n = 40000, d = 8 (3 x 12.8 GB)."""
+    n, d = 40000, 8
+    X, y, _ = synth(n, d, 404, "smooth")
+    F = np.ones((n, 1))
+    th, alpha = np.full(d, 0.5), 0.9
+    gamma = np.append(th, alpha)
+    rng = np.random.Generator(np.random.PCG64(44))
+    rows = np.sort(rng.choice(n, 1200, replace=False))
+    Rrows = _rows_of_R(X, rows, th, "matern3_2", alpha)
+    v = rng.standard_normal(n)
+    with capi.Engine(X, y, F, kernel="matern3_2", noise_model="nugget") as e:
+        val, g, info = e.objective("LL", gamma, with_info=True)
+        assert info["n_jitter"] == 0 and np.isfinite(val) and g.size == d + 1
+        L = e.export("L")
+        w = L.T @ v
+        assert relerr_vec(L[rows] @ w, Rrows @ v) < 1e-12
+        # sum log diag L as the engine reported it, against the exported factor
+        assert relerr(info["sum_log_diagL"], float(np.sum(np.log(np.diag(L))))) < 1e-13
+        del L, w
+        x = e.export("x")
+        r = e.eval_raw("LL", th, extra=alpha, want_grad=False)
+        resid = y - F @ r["betahat"]
+        assert relerr_vec(Rrows @ x, resid[rows]) < 1e-8
+        assert relerr(r["SSEstar"], float(resid @ x)) < 1e-9  # ||L^-1 e||^2 = e' R^-1 e
+        _fd_check(e, "LL", gamma, g, rng, 1e-5, 2e-5)
+
+
+def test_cfg3_loo_exp_n10000(capi):
+    """BASELINE config 3: Kriging('exp') leave-one-out at n = 10000, d = 6: value and diag(Q)-based vectors against
+    the oracle, the LOO errors against their definition at sampled points, the gradient against a central difference."""
+    import scipy.linalg as sl
+    n, d = 10000, 6
+    X, y, _ = synth(n, d, 303, "smooth")
+    F = np.ones((n, 1))
+    th = np.full(d, 0.5)
+    pb = ko.Problem(X=X, y=y, F=F, kernel="exp")
+    loo_o, _ = ko.leave_one_out(pb, th, want_grad=False)
+    rng = np.random.Generator(np.random.PCG64(33))
+    with capi.Engine(X, y, F, kernel="exp") as e:
+        val, g, info = e.objective("LOO", th, with_info=True)
+        assert info["n_jitter"] == 0
+        assert relerr(val, loo_o) < 1e-10
+        err = e.export("loo_err")
+        assert relerr(val, float(err @ err) / n) < 1e-13
+        # definition of leave-one-out: universal-kriging prediction of y_i from the other n - 1 points
+        R = ko.build_R(X, th, "exp")
+        for i in rng.choice(n, 2, replace=False):
+            keep = np.delete(np.arange(n), i)
+            c = sl.cho_factor(R[np.ix_(keep, keep)], lower=True, overwrite_a=True)
+            Ri_y, Ri_1, Ri_r = (sl.cho_solve(c, b) for b in (y[keep], np.ones(n - 1), R[keep, i]))
+            beta = (np.ones(n - 1) @ Ri_y) / (np.ones(n - 1) @ Ri_1)
+            pred = beta + R[keep, i] @ (Ri_y - beta * Ri_1)
+            assert abs((y[i] - pred) - err[i]) < 1e-8 * max(1.0, abs(y[i])), (i, y[i] - pred, err[i])
+            del c, Ri_y, Ri_1, Ri_r
+        del R
+        _fd_check(e, "LOO", th, g, rng, 1e-5, 1e-4)
+
+
+def test_cfg5_gauss_n5000_d20_vs_oracle_and_concurrent_starts(capi):
+    """BASELINE config 5 shape (gauss, n = 5000, d = 20): LL + gradient against the oracle, then a multistart fit
+    with several handles in flight on one GPU against the sequential fit (bitwise)."""
+    from libkriging_b200.kriging import Kriging
+    n, d = 5000, 20
+    X, y, _ = synth(n, d, 505, "smooth")
+    F = np.ones((n, 1))
+    th = np.full(d, 1.0)
+    pb = ko.Problem(X=X, y=y, F=F, kernel="gauss")
+    ll, g = ko.log_likelihood(pb, th)
+    with capi.Engine(X, y, F, kernel="gauss") as e:
+        v, gg, info = e.objective("LL", th, with_info=True)
+    assert info["rcond"] >= 1e-12
+    assert relerr(v, ll) < 1e-10
+    assert relerr_vec(gg, g) < 1e-10
+    fits = []
+    for con in (1, 4):
+        k = Kriging("gauss", concurrent_starts=con)
+        k.config.max_iteration = 4  # a short run is enough to compare trajectories
+        k.fit(y, X, optim="BFGS4", objective="LL")
+        fits.append((k.fit_log["best_start"], k.fit_log["objective"], k.fit_log["n_eval"], k.theta(), k.sigma2()))
+        k.close()
+    a, b = fits
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+    assert np.array_equal(a[3], b[3]) and a[4] == b[4]
