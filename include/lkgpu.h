@@ -104,6 +104,12 @@ int lkgpu_set_numerics(void* handle, double num_nugget, int max_inc_choldiag, do
 int lkgpu_theta_bounds(void* handle, double lower_factor, double upper_factor, int heuristic, double* lower,
                        double* upper);
 
+/* sigma2 bounds of NoiseModel::Heterogeneous (src/lib/Kriging.cpp:1784-1797):
+ *   *sigma2_variogram = 0.5 * mean(dy2[dX2 >= median(dX2)]) over the n^2 ordered pairs (diagonal included),
+ * by a radix select over the pair distances regenerated from X tiles -- neither dX nor dX2 nor dy2 exists.
+ * The caller forms extra_lower = 0.1 (s - max noise), extra_upper = 10 (s - min noise) (:1798-1799). */
+int lkgpu_sigma2_variogram(void* handle, double* sigma2_variogram);
+
 /* One objective evaluation = populate_Model (src/lib/KrigingImpl.cpp:73-125)
  * + the objective-specific reductions.  theta: [d]; extra = alpha (nugget) or
  * sigma2 (hetero), ignored for none.  sigma2_for_lmp unused unless LMP. */

@@ -57,6 +57,7 @@ def lib():
     L.lkgpu_set_numerics.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int]
     L.lkgpu_set_params.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]
     L.lkgpu_theta_bounds.argtypes = [vp, C.c_double, C.c_double, C.c_int, _dp, _dp]
+    L.lkgpu_sigma2_variogram.argtypes = [vp, _dp]
     L.lkgpu_eval.argtypes = [vp, C.c_int, _dp, C.c_double, C.c_int, C.POINTER(LkgpuOut)]
     L.lkgpu_objective_fun.argtypes = [vp, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, C.POINTER(LkgpuOut)]
     L.lkgpu_export.argtypes = [vp, C.c_int, _dp]
@@ -146,6 +147,11 @@ class Engine:
         up = np.empty(self.d)
         _check(lib().lkgpu_theta_bounds(self._h, lower_factor, upper_factor, int(heuristic), _ptr(lo), _ptr(up)))
         return lo, up
+
+    def sigma2_variogram(self) -> float:
+        v = C.c_double(0.0)
+        _check(lib().lkgpu_sigma2_variogram(self._h, C.byref(v)))
+        return v.value
 
     def eval_raw(self, objective, theta, extra=1.0, want_grad=True):
         """lkgpu_eval: the raw device reductions (dict)."""

@@ -23,6 +23,7 @@
 #include "potrf_panel.cuh"
 #include "trsv.cuh"
 #include "trsv_wave.cuh"
+#include "variogram.cuh"
 
 using namespace lk;
 
@@ -1055,6 +1056,76 @@ struct Engine {
     }
   }
 
+  // ---- sigma2 bounds of NoiseModel::Heterogeneous (f2; Kriging.cpp:1784-1797): variogram.cuh ----
+  double sigma2_variogram() {
+    CUDA_CHECK(cudaSetDevice(device));
+    const int t = (n + PT - 1) / PT;
+    const int ntiles = t * (t + 1) / 2;
+    const int grid = std::min(ntiles, 2 * sm_count);
+    const size_t smem = (size_t)(2 * d * PT + 2 * PT) * 8;
+    if (smem > 48 * 1024) {
+      CUDA_CHECK(cudaFuncSetAttribute(vario_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_CHECK(cudaFuncSetAttribute(vario_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    unsigned long long* dhist = dalloc<unsigned long long>(VG_BINS);
+    std::vector<unsigned long long> hist(VG_BINS);
+    const unsigned long long total = (unsigned long long)n * (unsigned long long)n;
+    // key of the element of 0-based rank r in the sorted multiset of all n^2 ordered-pair distances;
+    // *below = number of elements strictly smaller than that key
+    auto select = [&](unsigned long long r, unsigned long long* below) -> unsigned long long {
+      unsigned long long prefix = 0, skipped = 0;
+      int hi_shift = 64;
+      while (hi_shift > 0) {
+        const int width = std::min(VG_DIGIT_BITS, hi_shift);
+        const int shift = hi_shift - width;
+        CUDA_CHECK(cudaMemsetAsync(dhist, 0, VG_BINS * sizeof(unsigned long long), s_main));
+        ++launches;
+        vario_hist_kernel<<<grid, PAIR_THREADS, smem, s_main>>>(dX, n, d, prefix, hi_shift, shift, (1u << width) - 1u, dhist,
+                                                              ntiles);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(hist.data(), dhist, VG_BINS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_main));
+        CUDA_CHECK(cudaStreamSynchronize(s_main));
+        for (auto& h : hist) h *= 2ull;               // (i, j) and (j, i)
+        if (prefix == 0) hist[0] += (unsigned long long)n;  // the diagonal: n zeros
+        int b = 0;
+        while (b < (1 << width) - 1 && r >= hist[b]) {
+          r -= hist[b];
+          skipped += hist[b];
+          ++b;
+        }
+        if (r >= hist[b]) throw LkError{"lkgpu: radix select lost its rank (internal error)"};
+        prefix = (prefix << width) | (unsigned long long)b;
+        hi_shift = shift;
+      }
+      if (below) *below = skipped;
+      return prefix;
+    };
+    auto as_double = [](unsigned long long k) {
+      double v;
+      memcpy(&v, &k, 8);
+      return v;
+    };
+    const unsigned long long half = total / 2;
+    unsigned long long below = 0;
+    const double val1 = as_double(select(half, &below));  // op_median::direct_median: *nth
+    double med = val1;
+    if (total % 2 == 0) {
+      // val2 = max of the lower half = rank half - 1: the same key unless `half` is the first of its run
+      const double val2 = (below < half) ? val1 : as_double(select(half - 1, nullptr));
+      med = val1 + (val2 - val1) / 2.0;  // op_mean::robust_mean
+    }
+    launches += 2;
+    vario_sum_kernel<<<grid, PAIR_THREADS, smem, s_main>>>(dX, dy, n, d, med, dpartial, ntiles);
+    sum_partials_kernel<<<1, 32, 0, s_main>>>(dpartial, grid, 2, 2, dscal + SC_BOUNDS);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(hpin, dscal + SC_BOUNDS, 16, cudaMemcpyDeviceToHost, s_main));
+    CUDA_CHECK(cudaStreamSynchronize(s_main));
+    cudaFree(dhist);
+    const double sum = 2.0 * hpin[0];
+    const double cnt = 2.0 * hpin[1] + ((0.0 >= med) ? (double)n : 0.0);
+    return 0.5 * sum / cnt;
+  }
+
   // ---- theta bounds (a8) ----
   void theta_bounds(double lo_f, double up_f, int heuristic, double* lower, double* upper) {
     CUDA_CHECK(cudaSetDevice(device));
@@ -1163,6 +1234,13 @@ int lkgpu_theta_bounds(void* handle, double lower_factor, double upper_factor, i
   LK_TRY
   if (!handle || !lower || !upper) throw LkError{"lkgpu_theta_bounds: null argument"};
   static_cast<Engine*>(handle)->theta_bounds(lower_factor, upper_factor, heuristic, lower, upper);
+  LK_CATCH
+}
+
+int lkgpu_sigma2_variogram(void* handle, double* sigma2_variogram) {
+  LK_TRY
+  if (!handle || !sigma2_variogram) throw LkError{"lkgpu_sigma2_variogram: null argument"};
+  *sigma2_variogram = static_cast<Engine*>(handle)->sigma2_variogram();
   LK_CATCH
 }
 

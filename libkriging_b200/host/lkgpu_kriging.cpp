@@ -156,26 +156,11 @@ void Kriging::model_scalars(const arma::vec& theta, double extra, double* SSE, a
 }
 
 double Kriging::sigma2_variogram() const {
-  // Heterogeneous sigma2 bounds (Kriging.cpp:1784-1805): half the mean squared increment over the ordered pairs
-  // (diagonal included) whose squared distance is at least the median.  Host O(n^2).
-  const arma::uword n = m_X.n_rows;
-  arma::vec dX2(n * n), dy2(n * n);
-  for (arma::uword i = 0; i < n; ++i)
-    for (arma::uword j = 0; j < n; ++j) {
-      const arma::rowvec df = m_X.row(i) - m_X.row(j);
-      dX2[i * n + j] = arma::dot(df, df);
-      const double dy = m_y[i] - m_y[j];
-      dy2[i * n + j] = dy * dy;
-    }
-  const double med = arma::median(dX2);
-  double s = 0.0;
-  arma::uword cnt = 0;
-  for (arma::uword k = 0; k < n * n; ++k)
-    if (dX2[k] >= med) {
-      s += dy2[k];
-      ++cnt;
-    }
-  return 0.5 * s / (double)cnt;
+  // Heterogeneous sigma2 bounds (Kriging.cpp:1784-1797): half the mean squared increment over the ordered pairs
+  // (diagonal included) whose squared distance is at least the median -- on the device.
+  double v = 0.0;
+  check(lkgpu_sigma2_variogram(m_h, &v));
+  return v;
 }
 
 void Kriging::fit(const arma::vec& y, const arma::mat& X, const std::string& regmodel, bool normalize,

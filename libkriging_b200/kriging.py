@@ -45,6 +45,9 @@ class GpuBackend:
     def theta_bounds(self, lower_factor, upper_factor, heuristic):
         return self.engine.theta_bounds(lower_factor, upper_factor, heuristic)
 
+    def sigma2_variogram(self):
+        return self.engine.sigma2_variogram()
+
     def objective(self, name, gamma, want_grad):
         val, grad, info = self.engine.objective(name, gamma, want_grad, with_info=True)
         self.info = info
@@ -532,18 +535,10 @@ class Kriging:
         self._backend.model_scalars(self.m_theta, self._commit_extra)
 
     def _sigma2_variogram(self):
-        """Heterogeneous sigma2 bounds (Kriging.cpp:1784-1805): half the mean squared increment over the pairs
-        whose squared distance is at least the median (all n^2 ordered pairs, diagonal included).
-        Host O(n^2) loop kept on the CPU for now."""
-        Xn, yv = self.m_X, self.m_y
-        n = Xn.shape[0]
-        dX2 = np.empty((n, n))
-        for i0 in range(0, n, 2048):
-            blk = Xn[i0:i0 + 2048, None, :] - Xn[None, :, :]
-            dX2[i0:i0 + 2048] = np.sum(blk * blk, axis=2)
-        med = np.median(dX2)
-        dy2 = (yv[:, None] - yv[None, :]) ** 2
-        return 0.5 * float(np.mean(dy2[dX2 >= med]))
+        """Heterogeneous sigma2 bounds (Kriging.cpp:1784-1797): half the mean squared increment over the pairs
+        whose squared distance is at least the median (all n^2 ordered pairs, diagonal included) -- computed on the
+        device by lkgpu_sigma2_variogram (radix select over regenerated pair distances)."""
+        return float(self._backend.sigma2_variogram())
 
     def _gamma_full(self, theta):
         theta = np.asarray(theta, dtype=np.float64).ravel()

@@ -463,6 +463,33 @@ def theta_bounds(X, y, lower_factor=0.02, upper_factor=10.0, heuristic=True):
 # --------------------------------------------------------------------------
 # predict mean / stdev (src/lib/KrigingImpl.cpp:145-243), constant-sigma2 form
 # --------------------------------------------------------------------------
+def sigma2_variogram(X, y):
+    """sigma2 bounds of NoiseModel::Heterogeneous (src/lib/Kriging.cpp:1784-1797): dX2 = sum(dX % dX, 0) over all n^2
+    ordered pairs (Armadillo's arrayops::accumulate order: two interleaved accumulators), median as
+    op_median::direct_median (upper middle element + robust_mean with the lower one), then
+    0.5 * mean(dy2[dX2 >= median])."""
+    X = np.asarray(X, float)
+    y = np.asarray(y, float).ravel()
+    n, d = X.shape
+    dX2 = np.empty((n, n))
+    for i0 in range(0, n, 1024):
+        sq = (X[i0:i0 + 1024, None, :] - X[None, :, :]) ** 2
+        acc1 = np.zeros(sq.shape[:2])
+        acc2 = np.zeros(sq.shape[:2])
+        for k in range(0, d - 1, 2):
+            acc1 += sq[:, :, k]
+            acc2 += sq[:, :, k + 1]
+        if d % 2 == 1:
+            acc1 += sq[:, :, d - 1]
+        dX2[i0:i0 + 1024] = acc1 + acc2
+    flat = np.sort(dX2.ravel())
+    half = flat.size // 2
+    val1 = flat[half]
+    med = val1 + (flat[half - 1] - val1) / 2.0 if flat.size % 2 == 0 else val1
+    dy2 = (y[:, None] - y[None, :]) ** 2
+    return 0.5 * float(np.mean(dy2[dX2 >= med]))
+
+
 def predict(pb: Problem, theta, sigma2, Xn, Fn, m: KModel | None = None):
     if m is None:
         m = populate_model(pb, theta)

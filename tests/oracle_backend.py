@@ -21,6 +21,9 @@ class OracleBackend:
     def theta_bounds(self, lower_factor, upper_factor, heuristic):
         return ko.theta_bounds(self.pb.X, self.pb.y, lower_factor, upper_factor, heuristic)
 
+    def sigma2_variogram(self):
+        return ko.sigma2_variogram(self.pb.X, self.pb.y)
+
     def objective(self, name, gamma, want_grad):
         self.n_objective_calls += 1
         if name == "LL":

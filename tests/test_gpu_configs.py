@@ -122,3 +122,26 @@ def test_cfg5_gauss_n5000_d20_vs_oracle_and_concurrent_starts(capi):
     a, b = fits
     assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
     assert np.array_equal(a[3], b[3]) and a[4] == b[4]
+
+
+@pytest.mark.parametrize("n,d,seed", [(1, 2, 1), (2, 1, 2), (7, 3, 3), (64, 2, 4), (65, 5, 5), (300, 4, 6), (1001, 7, 7),
+                                      (2500, 10, 8)])
+def test_sigma2_variogram_vs_oracle(capi, n, d, seed):
+    """the Heterogeneous sigma2 bound (median of n^2 pair distances by radix select on the device)
+    against the oracle's restatement of Kriging.cpp:1784-1797 (sort-based), n^2 even and odd, ragged tiles."""
+    X, y, noise = synth(n, d, 600 + seed, "smooth")
+    with capi.Engine(X, y, np.ones((n, 1)), kernel="gauss", noise_model="hetero", noise=noise) as e:
+        s = e.sigma2_variogram()
+    assert relerr(s, ko.sigma2_variogram(X, y)) < 1e-12 if n > 1 else s == 0.0 or np.isnan(s)
+
+
+def test_sigma2_variogram_with_duplicates(capi):
+    """More than half of the pairs at distance zero (replicated design points): the median is 0 and every pair,
+    diagonal included, enters the mean."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    X = np.repeat(rng.random((3, 2)), 40, axis=0)[:100]
+    X[:70] = X[0]
+    y = rng.standard_normal(100)
+    with capi.Engine(X, y, np.ones((100, 1)), kernel="gauss", noise_model="hetero", noise=np.full(100, 0.1)) as e:
+        s = e.sigma2_variogram()
+    assert relerr(s, ko.sigma2_variogram(X, y)) < 1e-12

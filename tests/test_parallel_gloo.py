@@ -59,7 +59,7 @@ def test_sharded_multistart_equals_single_process():
     from libkriging_b200.kriging import Kriging
     from tests.oracle_backend import OracleBackend
     X, y, _ = synth(50, 2, 5, "smooth")
-    k = Kriging("matern5_2", backend_factory=OracleBackend)
+    k = Kriging("matern5_2", backend_factory=OracleBackend, concurrent_starts=1)
     k.fit(y, X, optim="BFGS4")
     for rank, theta, s2, best, local, ncalls in out:
         assert theta == k.theta().tolist() and s2 == k.sigma2() and best == k.fit_log["best_start"]
