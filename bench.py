@@ -344,6 +344,10 @@ def run_b200_arm(args):
                "starts": int(k.fit_log["multistart"]), "best_start": int(k.fit_log["best_start"]),
                "LL_at_fit": float(k.fit_log["objective"]) * -1.0, "theta": [float(t) for t in k.theta()],
                "sigma2": float(k.sigma2())}
+        st = getattr(k._backend, "stats", None)
+        if st:  # this rank's handle: objective calls, jitter-ladder rungs climbed, device time inside the evaluations
+            fit.update(evals_this_rank=int(st["evals"]), jitter_rungs_this_rank=int(st["jitter_rungs"]),
+                       device_ms_this_rank=float(st["device_ms"]))
         k.close()
     eng.close()
 

@@ -143,6 +143,28 @@ int lkgpu_predict(void* handle, int m, const double* Xn, const double* Fn, const
 /* Replace X / y / F / noise of an existing handle (same n, d, p). */
 int lkgpu_set_data(void* handle, const double* X, const double* y, const double* F, const double* noise);
 
+/* The reference keeps the committed model (m_T, m_M, m_z, m_circ, m_beta; commit at src/lib/Kriging.cpp:2156-2173)
+ * apart from the per-evaluation KModel workspaces, so objective calls at other points never disturb predict().
+ * lkgpu_commit_model snapshots the model of the last evaluation into a device-side store (one extra n*n buffer,
+ * allocated on the first commit); lkgpu_restore_model makes it the live model again (a device-to-device copy, no
+ * re-evaluation; a no-op when nothing was evaluated since).  lkgpu_append_data extends the committed model. */
+int lkgpu_commit_model(void* handle);
+int lkgpu_restore_model(void* handle);
+
+/* Kriging::update, data side (src/lib/Kriging.cpp:2476-2491; KrigingImpl::update_no_refit_impl,
+ * src/lib/KrigingImpl.cpp:576-610): append n_u observations (X_u: n_u*d column-major, normalised with the model's
+ * own centre / scale; y_u: n_u; F_u: n_u*p; noise_u: n_u or NULL) to the handle's data set.  The device workspaces
+ * are re-created for n + n_u rows and the Cholesky factor of the last evaluation -- the caller makes that the
+ * committed model, the reference's m_T -- is kept, so that the next lkgpu_eval / lkgpu_objective_fun at the SAME
+ * theta (and alpha | sigma2) runs as the block extension of LinearAlgebra::update_cholCov / chol_block
+ * (src/lib/LinearAlgebra.cpp:206-299) instead of a factorisation from scratch: populate_Model's `update_eligible`
+ * (src/lib/Kriging.cpp:170-188), including chol_block's fall-back to a full safe_chol_lower when the ladder on the
+ * Schur complement is exhausted.  An evaluation at any other point factors from scratch and drops the kept factor. */
+int lkgpu_append_data(void* handle, int n_u, const double* X_u, const double* y_u, const double* F_u,
+                      const double* noise_u);
+/* 1 if the last evaluation on this handle ran as a block extension of a kept factor, else 0 */
+int lkgpu_last_eval_was_update(void* handle);
+
 void lkgpu_destroy(void* handle);
 const char* lkgpu_last_error(void);
 int lkgpu_abi_version(void);

@@ -63,6 +63,11 @@ def lib():
     L.lkgpu_export.argtypes = [vp, C.c_int, _dp]
     L.lkgpu_predict.argtypes = [vp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp]
     L.lkgpu_set_data.argtypes = [vp, _dp, _dp, _dp, _dp]
+    L.lkgpu_append_data.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp]
+    L.lkgpu_commit_model.argtypes = [vp]
+    L.lkgpu_restore_model.argtypes = [vp]
+    L.lkgpu_last_eval_was_update.argtypes = [vp]
+    L.lkgpu_last_eval_was_update.restype = C.c_int
     L.lkgpu_destroy.argtypes = [vp]
     L.lkgpu_destroy.restype = None
     L.lkgpu_last_error.restype = C.c_char_p
@@ -141,6 +146,31 @@ class Engine:
         F = np.asfortranarray(np.asarray(F, dtype=np.float64).reshape(X.shape[0], -1))
         nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64).ravel()
         _check(lib().lkgpu_set_data(self._h, _ptr(X), _ptr(y), _ptr(F), _ptr(nz)))
+
+    def append_data(self, X_u, y_u, F_u, noise_u=None):
+        """lkgpu_append_data: extend the data set by n_u observations; the factor of the last evaluation is kept
+        for a block extension at the same theta (Kriging::update)."""
+        X_u = np.asfortranarray(np.asarray(X_u, dtype=np.float64).reshape(-1, self.d))
+        n_u = X_u.shape[0]
+        y_u = np.ascontiguousarray(y_u, dtype=np.float64).ravel()
+        F_u = np.asfortranarray(np.asarray(F_u, dtype=np.float64).reshape(n_u, -1))
+        if y_u.size != n_u or F_u.shape[1] != self.p:
+            raise LkgpuError("append_data: y_u / F_u do not match X_u")
+        nz = None if noise_u is None else np.ascontiguousarray(noise_u, dtype=np.float64).ravel()
+        _check(lib().lkgpu_append_data(self._h, n_u, _ptr(X_u), _ptr(y_u), _ptr(F_u), _ptr(nz)))
+        self.n += n_u
+
+    def commit_model(self):
+        """Snapshot the model of the last evaluation as the committed model (m_T, m_M, m_z, ... of the reference)."""
+        _check(lib().lkgpu_commit_model(self._h))
+
+    def restore_model(self):
+        """Make the committed model the live one again (device-to-device copy; no-op if nothing ran since)."""
+        _check(lib().lkgpu_restore_model(self._h))
+
+    @property
+    def last_eval_was_update(self) -> bool:
+        return bool(lib().lkgpu_last_eval_was_update(self._h))
 
     def theta_bounds(self, lower_factor=0.02, upper_factor=10.0, heuristic=True):
         lo = np.empty(self.d)

@@ -22,6 +22,15 @@ __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Writer-side fence for global data that a LATER kernel reads through TMA (async proxy): make this thread's generic-
+// proxy stores visible at gpu scope and order them before async-proxy accesses.  Measured on B200: with several
+// handles running concurrently on one GPU (other grids resident between the producing and the consuming kernel),
+// a TMA load in the next kernel of the same stream could return data from before the previous kernel's last
+// epilogue stores (~1 % of the evaluations; never with a single handle); with this fence after the stores, never.
+__device__ __forceinline__ void fence_writes_for_tma() {
+  __threadfence();
+  fence_proxy_async();
+}
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

@@ -87,19 +87,25 @@ __device__ __forceinline__ void stage_x(const double* __restrict__ X, int n, int
 // ---------------------------------------------------------------------------
 // K1: A[i, j] = alpha * rho_ij (i != j), A[i, i] = 1 (+ noise_i * inv_sigma2) + diag_add ; padding = identity.
 // Tiles with ti >= tj only; the diagonal tile is written in full (symmetric).
+// Partial builds (block extension of a kept factor, LinearAlgebra::update_cholCov, LinearAlgebra.cpp:206-243):
+// tile = tri_tile(blockIdx-strided id + id0) shifted by `shift` on both axes -- id0 = t0 (t0 + 1) / 2, shift = 0
+// builds the row tiles >= t0 over all their columns; id0 = 0, shift = t0 builds the lower-right block only.
+// Rows below diag_split receive diag_add_lo (the jitter the kept factor was accepted with) instead of diag_add.
 // ---------------------------------------------------------------------------
 template <int KERNEL>
 __global__ void __launch_bounds__(PAIR_THREADS)
 cov_build_kernel(const double* __restrict__ X, int n, int d, const __grid_constant__ KernelParams kp, double alpha,
                  const double* __restrict__ noise, double inv_sigma2, double diag_add, double* __restrict__ A,
-                 long long ld, int ntiles) {
+                 long long ld, int ntiles, int id0, int shift, int diag_split, double diag_add_lo) {
   extern __shared__ double sm[];
   double* xi = sm;
   double* xj = sm + d * PT;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int ti, tj;
-    tri_tile(tile, ti, tj);
+    tri_tile(tile + id0, ti, tj);
+    ti += shift;
+    tj += shift;
     __syncthreads();
     stage_x(X, n, d, kp, ti * PT, xi);
     stage_x(X, n, d, kp, tj * PT, xj);
@@ -134,7 +140,7 @@ cov_build_kernel(const double* __restrict__ X, int n, int d, const __grid_consta
         if (i >= n || j >= n) {
           r = (i == j) ? 1.0 : 0.0;
         } else if (i == j) {
-          r = 1.0 + (noise ? noise[i] * inv_sigma2 : 0.0) + diag_add;
+          r = 1.0 + (noise ? noise[i] * inv_sigma2 : 0.0) + (i < diag_split ? diag_add_lo : diag_add);
         } else {
           r = alpha * corr_finish<KERNEL>(es[a][b], pr[a][b]);
         }
@@ -145,6 +151,7 @@ cov_build_kernel(const double* __restrict__ X, int n, int d, const __grid_consta
       *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
     }
   }
+  fence_writes_for_tma();  // A is a TMA operand of the factorisation's GEMMs
 }
 
 // ---------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 //   Bv N x (p+1) : [F | y] -> [Fstar | ystar] ;  Ev, Xv : N vectors (Estar, x)
 // No CPU fallback anywhere: every entry point needs a CUDA device.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +31,8 @@ using namespace lk;
 namespace {
 
 thread_local std::string g_last_error;
+// live handles per device: the sweeps choose their kernel by it (see Engine::solve_fwd)
+std::atomic<int> g_live_handles[64];
 
 struct LkError {
   std::string msg;
@@ -145,6 +148,36 @@ __global__ void pad_copy_kernel(const double* __restrict__ src, long long lds, i
   dst[(long long)c * ldd + r] = (r < n) ? src[(long long)c * lds + r] : 0.0;
 }
 
+// Device-side fills and copies in the evaluation path are kernels, not cudaMemsetAsync / cudaMemcpyAsync: with
+// several handles running concurrently on one GPU, copy-engine writes were observed to become visible to the next
+// kernel of the same stream late (stale right-hand sides in ~1 % of the sweeps); stores from a kernel followed by a
+// gpu-scope fence were not.
+__global__ void zero_ints_kernel(int* p, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) p[i] = 0;
+  __threadfence();
+}
+__global__ void fill_zero_kernel(double* __restrict__ p, long long count) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    p[i] = 0.0;
+  fence_writes_for_tma();
+}
+__global__ void copy_diag_blocks_kernel(double* __restrict__ dst, long long dst_ld, long long dst_blk,
+                                       const double* __restrict__ src, long long src_ld, long long src_blk) {
+  double* d_ = dst + blockIdx.x * dst_blk;
+  const double* s_ = src + blockIdx.x * src_blk;
+  for (int e = threadIdx.x; e < BLK * BLK; e += blockDim.x) {
+    const int c = e / BLK, r = e % BLK;
+    d_[c * dst_ld + r] = s_[c * src_ld + r];
+  }
+  fence_writes_for_tma();
+}
+__global__ void copy_kernel(double* __restrict__ dst, const double* __restrict__ src, long long count) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+  fence_writes_for_tma();
+}
+
 __global__ void scale_signs_kernel(double* x, int n, int mode) {
   // dlacn2 helpers: mode 0: x = sign(x) ; mode 1: altsgn ramp
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,6 +199,10 @@ struct Engine {
   bool debug_simple = false;
   bool use_lookahead = true;
   bool use_step_trsv = false;
+  bool wave_always = false;
+  int wave_grid_cap = 0;  // LKGPU_WAVE_GRID=k: at most k CTAs per sweep (fault localisation)
+  bool no_persistent = false;  // LKGPU_NO_PERSISTENT=1: one CTA per tile everywhere (fault localisation)
+  bool use_abort = true;  // LKGPU_NO_ABORT=1: failed Cholesky attempts run to the end (fault localisation)
   int outer_panels = 4;  // Cholesky outer block = outer_panels * 128 columns (LKGPU_OUTER_PANELS)
   // numerics (LinearAlgebra statics of the reference)
   double num_nugget = 1e-10, min_rcond = 1e-18;
@@ -216,9 +253,30 @@ struct Engine {
   double last_alpha = 1.0, last_inv_sigma2 = 0.0, last_diag_add = 0.0;
   int last_n_jitter = 0;
   std::vector<double> last_theta;
+  // factor kept across lkgpu_append_data (the reference's m_T while m_X has more rows than m_T)
+  int keep_n = 0;
+  std::vector<double> keep_theta;
+  double keep_alpha = 1.0, keep_inv_sigma2 = 0.0, keep_diag_add = 0.0;
+  bool last_was_update = false, last_mixed_jitter = false;
+  // committed model: the reference's members m_T, m_M, m_z, m_circ, m_beta (commit at Kriging.cpp:2156-2173), which
+  // live apart from the per-evaluation KModel workspaces.  One extra n x n buffer, allocated on the first commit.
+  struct Committed {
+    bool valid = false, have_x = false, mixed = false;
+    double *L = nullptr, *D = nullptr, *Bv = nullptr, *Ev = nullptr, *Xv = nullptr, *Rstar = nullptr, *beta = nullptr,
+           *logdet = nullptr;
+    std::vector<double> theta;
+    double alpha = 1.0, inv_sigma2 = 0.0, diag_add = 0.0;
+    int n_jitter = 0;
+  } cm;
+  bool live_is_committed = false;
 
-  ~Engine() { release(); }
-  void release() {
+  bool registered = false;
+  ~Engine() {
+    release();
+    if (registered) g_live_handles[device & 63].fetch_sub(1);
+  }
+  // everything whose size depends on n (lkgpu_append_data re-creates these for the extended data set)
+  void release_sized() {
     cudaSetDevice(device);
     double* bufs[] = {dX, dy, dF, dnoise, A, W, V, Bv, Ev, Xv, Tv, Uv, Zv, Qv, dS2loo, dErr, dSqrtC, dEs, Q1, Q2, dsmall,
                       logdet_blocks, dscal, dpartial, dcolsum, dRstar, dbeta};
@@ -233,18 +291,32 @@ struct Engine {
     if (hpin) cudaFreeHost(hpin);
     for (auto e : ev_panel) cudaEventDestroy(e);
     for (auto e : ev_upd) cudaEventDestroy(e);
-    for (auto& e : ev_t)
-      if (e) cudaEventDestroy(e);
-    if (ev_misc) cudaEventDestroy(ev_misc);
-    if (s_main) cudaStreamDestroy(s_main);
-    if (s_upd) cudaStreamDestroy(s_upd);
+    {
+      double* cbufs[] = {cm.L, cm.D, cm.Bv, cm.Ev, cm.Xv, cm.Rstar, cm.beta, cm.logdet};
+      for (double* b : cbufs)
+        if (b) cudaFree(b);
+      cm.L = cm.D = cm.Bv = cm.Ev = cm.Xv = cm.Rstar = cm.beta = cm.logdet = nullptr;
+      cm.valid = false;
+      live_is_committed = false;
+    }
     dX = dy = dF = dnoise = A = W = V = Bv = Ev = Xv = Tv = Uv = logdet_blocks = dscal = dpartial = dcolsum = dRstar = dbeta = nullptr;
     Zv = Qv = dS2loo = dErr = dSqrtC = dEs = Q1 = Q2 = dsmall = nullptr;
     dinfo = nullptr;
     trtri_tables = lauum_table = loo_table = nullptr;
+    loo_tiles = lauum_tiles = 0;
     hpin = nullptr;
     ev_panel.clear();
     ev_upd.clear();
+  }
+  void release() {
+    release_sized();
+    for (auto& e : ev_t)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : ev_t) e = nullptr;
+    if (ev_misc) cudaEventDestroy(ev_misc);
+    ev_misc = nullptr;
+    if (s_main) cudaStreamDestroy(s_main);
+    if (s_upd) cudaStreamDestroy(s_upd);
     s_main = s_upd = nullptr;
   }
 
@@ -282,29 +354,53 @@ struct Engine {
     const char* nla = getenv("LKGPU_NO_LOOKAHEAD");
     use_lookahead = !(nla && nla[0] == '1');
     if (const char* op = getenv("LKGPU_OUTER_PANELS")) outer_panels = std::max(1, std::min(16, atoi(op)));
+    if (const char* wg = getenv("LKGPU_WAVE_GRID")) wave_grid_cap = atoi(wg);
+    if (const char* wa = getenv("LKGPU_WAVE_ALWAYS")) wave_always = wa[0] == '1';
+    const char* npe = getenv("LKGPU_NO_PERSISTENT");
+    no_persistent = npe && npe[0] == '1';
+    const char* nab = getenv("LKGPU_NO_ABORT");
+    use_abort = !(nab && nab[0] == '1');
     const char* stv = getenv("LKGPU_STEP_TRSV");
     use_step_trsv = stv && stv[0] == '1';
 
+    int lo_pri = 0, hi_pri = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    if (const char* npr = getenv("LKGPU_NO_PRIORITY"); npr && npr[0] == '1') hi_pri = lo_pri;  // fault localisation
+    CUDA_CHECK(cudaStreamCreateWithPriority(&s_main, cudaStreamNonBlocking, hi_pri));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&s_upd, cudaStreamNonBlocking, lo_pri));
+    for (auto& ev : ev_t) CUDA_CHECK(cudaEventCreate(&ev));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_misc, cudaEventDisableTiming));
+#define LK_WAVE_ATTR(BW, NQ_) \
+  CUDA_CHECK(cudaFuncSetAttribute(trsv_wave_kernel<BW, NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_smem_bytes(NQ_)))
+    LK_WAVE_ATTR(false, 1); LK_WAVE_ATTR(false, 2); LK_WAVE_ATTR(false, 4); LK_WAVE_ATTR(false, 8);
+    LK_WAVE_ATTR(true, 1); LK_WAVE_ATTR(true, 2); LK_WAVE_ATTR(true, 4); LK_WAVE_ATTR(true, 8);
+#undef LK_WAVE_ATTR
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
+    alloc_sized(noise != nullptr);
+    set_data(X, y, F, noise);
+    CUDA_CHECK(cudaStreamSynchronize(s_main));
+    g_live_handles[device & 63].fetch_add(1);
+    registered = true;
+  }
+
+  // device workspaces, tensor maps and tile plans for the current n (a1: KModel)
+  void alloc_sized(bool with_noise) {
     N = ((n + BLK - 1) / BLK) * BLK;
     nb = N / BLK;
     ld = N;
-    int lo_pri = 0, hi_pri = 0;
-    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-    CUDA_CHECK(cudaStreamCreateWithPriority(&s_main, cudaStreamNonBlocking, hi_pri));
-    CUDA_CHECK(cudaStreamCreateWithPriority(&s_upd, cudaStreamNonBlocking, lo_pri));
     ev_panel.resize(nb);
     ev_upd.resize(nb);
     for (int i = 0; i < nb; ++i) {
       CUDA_CHECK(cudaEventCreateWithFlags(&ev_panel[i], cudaEventDisableTiming));
       CUDA_CHECK(cudaEventCreateWithFlags(&ev_upd[i], cudaEventDisableTiming));
     }
-    for (auto& ev : ev_t) CUDA_CHECK(cudaEventCreate(&ev));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev_misc, cudaEventDisableTiming));
-
     dX = dalloc<double>((size_t)n * d);
     dy = dalloc<double>(n);
     dF = dalloc<double>((size_t)n * p);
-    if (noise) dnoise = dalloc<double>(n);
+    if (with_noise) dnoise = dalloc<double>(n);
     A = dalloc<double>((size_t)N * N);
     W = dalloc<double>((size_t)N * N);
     V = dalloc<double>((size_t)N * N);
@@ -336,8 +432,6 @@ struct Engine {
     CUDA_CHECK(cudaMemsetAsync(W, 0, (size_t)N * N * 8, s_main));
     CUDA_CHECK(cudaMemsetAsync(V, 0, (size_t)N * N * 8, s_main));
     CUDA_CHECK(cudaMemsetAsync(A, 0, (size_t)N * N * 8, s_main));
-    set_data(X, y, F, noise);
-
     auto maps_of = [&](double* buf) {
       return MatMaps{make_map(buf, N, N, ld, 16, 16), make_map(buf, N, N, ld, 16, 64),
                      make_map(buf, N, N, ld, 128, 32, false), make_map(buf, N, N, ld, 16, 128)};
@@ -346,18 +440,141 @@ struct Engine {
     mapW = maps_of(W);
     mapV = maps_of(V);
     wave_ctl = dalloc<int>(nb + 1);
-#define LK_WAVE_ATTR(BW, NQ_) \
-  CUDA_CHECK(cudaFuncSetAttribute(trsv_wave_kernel<BW, NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_smem_bytes(NQ_)))
-    LK_WAVE_ATTR(false, 1); LK_WAVE_ATTR(false, 2); LK_WAVE_ATTR(false, 4); LK_WAVE_ATTR(false, 8);
-    LK_WAVE_ATTR(true, 1); LK_WAVE_ATTR(true, 2); LK_WAVE_ATTR(true, 4); LK_WAVE_ATTR(true, 8);
-#undef LK_WAVE_ATTR
-
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_CHECK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
     build_plans();
+  }
+
+  // ---- commit / restore (the reference moves km.L, km.Fstar, ... into m_T, m_M, ...: Kriging.cpp:2156-2173) ----
+  void copy_diag_blocks(double* dst, long long dst_ld, long long dst_blk, const double* src, long long src_ld,
+                        long long src_blk) {
+    ++launches;
+    copy_diag_blocks_kernel<<<nb, 256, 0, s_main>>>(dst, dst_ld, dst_blk, src, src_ld, src_blk);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  void commit() {
+    CUDA_CHECK(cudaSetDevice(device));
+    if (!have_model) throw LkError{"lkgpu_commit_model: no evaluation has been run on this handle"};
+    if (!cm.L) {
+      cm.L = dalloc<double>((size_t)N * N);
+      cm.D = dalloc<double>((size_t)nb * BLK * BLK);
+      cm.Bv = dalloc<double>((size_t)N * (p + 1));
+      cm.Ev = dalloc<double>(N);
+      cm.Xv = dalloc<double>(N);
+      cm.Rstar = dalloc<double>((size_t)p * p);
+      cm.beta = dalloc<double>(p);
+      cm.logdet = dalloc<double>(nb);
+    }
+    dev_copy(cm.L, A, (long long)N * N);
+    copy_diag_blocks(cm.D, BLK, (long long)BLK * BLK, W, ld, (long long)BLK * ld + BLK);
+    dev_copy(cm.Bv, Bv, (long long)N * (p + 1));
+    dev_copy(cm.Ev, Ev, N);
+    dev_copy(cm.Xv, Xv, N);
+    dev_copy(cm.Rstar, dRstar, (long long)p * p);
+    dev_copy(cm.beta, dbeta, p);
+    dev_copy(cm.logdet, logdet_blocks, nb);
     CUDA_CHECK(cudaStreamSynchronize(s_main));
+    cm.theta = last_theta;
+    cm.alpha = last_alpha;
+    cm.inv_sigma2 = last_inv_sigma2;
+    cm.diag_add = last_diag_add;
+    cm.n_jitter = last_n_jitter;
+    cm.mixed = last_mixed_jitter;
+    cm.have_x = have_x;
+    cm.valid = true;
+    live_is_committed = true;
+  }
+  void restore() {
+    CUDA_CHECK(cudaSetDevice(device));
+    if (!cm.valid) throw LkError{"lkgpu_restore_model: no committed model on this handle"};
+    if (live_is_committed) return;
+    dev_copy(A, cm.L, (long long)N * N);
+    copy_diag_blocks(W, ld, (long long)BLK * ld + BLK, cm.D, BLK, (long long)BLK * BLK);
+    dev_copy(Bv, cm.Bv, (long long)N * (p + 1));
+    dev_copy(Ev, cm.Ev, N);
+    dev_copy(Xv, cm.Xv, N);
+    dev_copy(dRstar, cm.Rstar, (long long)p * p);
+    dev_copy(dbeta, cm.beta, p);
+    dev_copy(logdet_blocks, cm.logdet, nb);
+    CUDA_CHECK(cudaStreamSynchronize(s_main));
+    last_theta = cm.theta;
+    last_alpha = cm.alpha;
+    last_inv_sigma2 = cm.inv_sigma2;
+    last_diag_add = cm.diag_add;
+    last_n_jitter = cm.n_jitter;
+    last_mixed_jitter = cm.mixed;
+    have_model = true;
+    have_x = cm.have_x;
+    have_W = have_V = have_loo = false;  // W holds the diagonal-block inverses only; L^-1 / R^-1 are re-derived on demand
+    keep_n = 0;
+    live_is_committed = true;
+  }
+
+  // ---- Kriging::update, data side (Kriging.cpp:2476-2491, KrigingImpl.cpp:576-610): append n_u observations.
+  // The workspaces are re-created for n + n_u rows.  The factor of the last evaluation (the committed model: the
+  // reference's m_T) is kept -- its whole 128-column panels; the rows of a partial last panel are re-derived -- so
+  // that the next evaluation at the SAME (theta, extra) runs as a block extension (factor_update below) instead of
+  // a factorisation from scratch: populate_Model's `update_eligible` (Kriging.cpp:170-188).
+  void append(int n_u, const double* X_u, const double* y_u, const double* F_u, const double* noise_u) {
+    CUDA_CHECK(cudaSetDevice(device));
+    if (n_u < 1) throw LkError{"lkgpu_append_data: need n_u >= 1"};
+    if (noise_model == LKGPU_NOISE_HETERO && !noise_u) throw LkError{"lkgpu_append_data: heterogeneous noise needs noise_u"};
+    if (cm.valid && !live_is_committed) restore();  // the factor that is extended is the committed one (m_T)
+    CUDA_CHECK(cudaStreamSynchronize(s_main));
+    CUDA_CHECK(cudaStreamSynchronize(s_upd));
+    const int n_old = n;
+    const long long ld_old = ld;
+    double *A_old = A, *W_old = W, *ldb_old = logdet_blocks, *X_old = dX, *y_old = dy, *F_old = dF, *nz_old = dnoise;
+    A = W = logdet_blocks = dX = dy = dF = dnoise = nullptr;
+    const bool keep = have_model;
+    release_sized();
+    auto free_old = [&]() {
+      double* olds[] = {A_old, W_old, ldb_old, X_old, y_old, F_old, nz_old};
+      for (double* b : olds)
+        if (b) cudaFree(b);
+    };
+    try {
+      n = n_old + n_u;
+      alloc_sized(nz_old != nullptr);
+      // data: column-major with the new column stride n
+      CUDA_CHECK(cudaMemcpy2DAsync(dX, (size_t)n * 8, X_old, (size_t)n_old * 8, (size_t)n_old * 8, d, cudaMemcpyDeviceToDevice, s_main));
+      CUDA_CHECK(cudaMemcpy2DAsync(dX + n_old, (size_t)n * 8, X_u, (size_t)n_u * 8, (size_t)n_u * 8, d, cudaMemcpyHostToDevice, s_main));
+      CUDA_CHECK(cudaMemcpy2DAsync(dF, (size_t)n * 8, F_old, (size_t)n_old * 8, (size_t)n_old * 8, p, cudaMemcpyDeviceToDevice, s_main));
+      CUDA_CHECK(cudaMemcpy2DAsync(dF + n_old, (size_t)n * 8, F_u, (size_t)n_u * 8, (size_t)n_u * 8, p, cudaMemcpyHostToDevice, s_main));
+      CUDA_CHECK(cudaMemcpyAsync(dy, y_old, (size_t)n_old * 8, cudaMemcpyDeviceToDevice, s_main));
+      CUDA_CHECK(cudaMemcpyAsync(dy + n_old, y_u, (size_t)n_u * 8, cudaMemcpyHostToDevice, s_main));
+      if (dnoise) {
+        CUDA_CHECK(cudaMemcpyAsync(dnoise, nz_old, (size_t)n_old * 8, cudaMemcpyDeviceToDevice, s_main));
+        if (noise_u) CUDA_CHECK(cudaMemcpyAsync(dnoise + n_old, noise_u, (size_t)n_u * 8, cudaMemcpyHostToDevice, s_main));
+        else CUDA_CHECK(cudaMemsetAsync(dnoise + n_old, 0, (size_t)n_u * 8, s_main));
+      }
+      for (int k = 0; k < d; ++k) {
+        const double* c = X_u + (size_t)k * n_u;
+        xmin[k] = std::min(xmin[k], *std::min_element(c, c + n_u));
+        xmax[k] = std::max(xmax[k], *std::max_element(c, c + n_u));
+      }
+      keep_n = 0;
+      // (a factor whose kept and appended rows were accepted with different jitter is not kept a second time:
+      //  the next evaluation factors from scratch, the reference's own fallback)
+      if (keep && !last_mixed_jitter) {
+        const int pb = n_old / BLK;
+        const size_t c0 = (size_t)pb * BLK;
+        if (c0 > 0) {
+          CUDA_CHECK(cudaMemcpy2DAsync(A, (size_t)ld * 8, A_old, (size_t)ld_old * 8, c0 * 8, c0, cudaMemcpyDeviceToDevice, s_main));
+          CUDA_CHECK(cudaMemcpy2DAsync(W, (size_t)ld * 8, W_old, (size_t)ld_old * 8, c0 * 8, c0, cudaMemcpyDeviceToDevice, s_main));
+          CUDA_CHECK(cudaMemcpyAsync(logdet_blocks, ldb_old, (size_t)pb * 8, cudaMemcpyDeviceToDevice, s_main));
+        }
+        keep_n = n_old;
+        keep_theta = last_theta;
+        keep_alpha = last_alpha;
+        keep_inv_sigma2 = last_inv_sigma2;
+        keep_diag_add = last_diag_add;
+      }
+      CUDA_CHECK(cudaStreamSynchronize(s_main));
+    } catch (...) {
+      free_old();
+      throw;
+    }
+    free_old();
+    have_model = have_W = have_V = have_x = have_loo = false;
   }
 
   void set_data(const double* X, const double* y, const double* F, const double* noise) {
@@ -367,6 +584,9 @@ struct Engine {
     if (noise && dnoise) CUDA_CHECK(cudaMemcpyAsync(dnoise, noise, (size_t)n * 8, cudaMemcpyHostToDevice, s_main));
     CUDA_CHECK(cudaStreamSynchronize(s_main));
     have_model = have_W = have_V = have_x = false;
+    keep_n = 0;
+    cm.valid = false;
+    live_is_committed = false;
     xmin.assign(d, 0.0);
     xmax.assign(d, 0.0);
     for (int k = 0; k < d; ++k) {
@@ -446,7 +666,7 @@ struct Engine {
       CUDA_CHECK(cudaGetLastError());
       return;
     }
-    int grid = persistent ? std::min(args.ntiles, 2 * sm_count) : args.ntiles;
+    int grid = (persistent && !no_persistent) ? std::min(args.ntiles, 2 * sm_count) : args.ntiles;
     if (layout == 0)
       gemm_dmma_kernel<false, false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mM.mm, mN.mm, args);
     else if (layout == 1)
@@ -474,19 +694,38 @@ struct Engine {
   }
 
   // ---- covariance build (a2) ----
-  void cov_build(double* dst, double alpha, double inv_sigma2, double diag_add, cudaStream_t st) {
+  // Full lower triangle (t0 = 0), or -- for the block extension of a kept factor -- the 64-row tiles >= t0 only:
+  // over all their columns (lower_right_only = false) or over the columns >= 64 t0 only (true).  Rows below
+  // diag_split get diag_add_lo on the diagonal (the jitter of the kept factor), the others diag_add.
+  void cov_build(double* dst, double alpha, double inv_sigma2, double diag_add, cudaStream_t st, int t0 = 0,
+                 bool lower_right_only = false, int diag_split = 0, double diag_add_lo = 0.0) {
     const int t = N / PT;
-    const int ntiles = t * (t + 1) / 2;
+    int ntiles, id0, shift;
+    if (lower_right_only) {
+      const int r = t - t0;
+      ntiles = r * (r + 1) / 2;
+      id0 = 0;
+      shift = t0;
+    } else {
+      id0 = t0 * (t0 + 1) / 2;
+      ntiles = t * (t + 1) / 2 - id0;
+      shift = 0;
+    }
+    if (ntiles <= 0) return;
     const int grid = std::min(ntiles, 8 * sm_count);
     const size_t smem = (size_t)2 * d * PT * 8;
     const double* nz = (noise_model == LKGPU_NOISE_HETERO) ? dnoise : nullptr;
     ++launches;
+#define LK_COV(K)                                                                                                     \
+  cov_build_kernel<K><<<grid, PAIR_THREADS, smem, st>>>(dX, n, d, kp, alpha, nz, inv_sigma2, diag_add, dst, ld, ntiles, \
+                                                        id0, shift, diag_split, diag_add_lo)
     switch (kernel) {
-      case 0: cov_build_kernel<0><<<grid, PAIR_THREADS, smem, st>>>(dX, n, d, kp, alpha, nz, inv_sigma2, diag_add, dst, ld, ntiles); break;
-      case 1: cov_build_kernel<1><<<grid, PAIR_THREADS, smem, st>>>(dX, n, d, kp, alpha, nz, inv_sigma2, diag_add, dst, ld, ntiles); break;
-      case 2: cov_build_kernel<2><<<grid, PAIR_THREADS, smem, st>>>(dX, n, d, kp, alpha, nz, inv_sigma2, diag_add, dst, ld, ntiles); break;
-      default: cov_build_kernel<3><<<grid, PAIR_THREADS, smem, st>>>(dX, n, d, kp, alpha, nz, inv_sigma2, diag_add, dst, ld, ntiles); break;
+      case 0: LK_COV(0); break;
+      case 1: LK_COV(1); break;
+      case 2: LK_COV(2); break;
+      default: LK_COV(3); break;
     }
+#undef LK_COV
     CUDA_CHECK(cudaGetLastError());
   }
 
@@ -503,24 +742,32 @@ struct Engine {
     a.ntiles = ncols * mt - ncols * (ncols - 1);
     return a;
   }
-  void cholesky() {
-    CUDA_CHECK(cudaMemsetAsync(dinfo, 0, 4 * sizeof(int), s_main));
+  // Every launch of an attempt carries dinfo as its abort flag: after the first non-positive pivot the remaining
+  // panels and updates are no-ops (the attempt is discarded by the ladder either way).
+  GemmArgs chol_gemm(GemmArgs a) {
+    a.abort_flag = use_abort ? dinfo : nullptr;
+    return a;
+  }
+  // Jstart > 0: the panels < Jstart already hold L (kept factor + row-block solve) and the trailing block
+  // [Jstart.., Jstart..] holds the Schur complement: chol_block's last step (LinearAlgebra.cpp:286).
+  void cholesky(int Jstart = 0) {
+    dev_zero_ints(dinfo, 4);
     const int OB = outer_panels;
     int last_upd = -1;
-    for (int J0 = 0; J0 < nb; J0 += OB) {
+    for (int J0 = Jstart; J0 < nb; J0 += OB) {
       const int J1 = std::min(nb, J0 + OB);
       const int c0 = J0 * BLK, c1 = J1 * BLK;
       for (int j = J0; j < J1; ++j) {
         const int jb = j * BLK;
         ++launches;
-        potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM_BYTES, s_main>>>(A, W, ld, jb, logdet_blocks, j, dinfo);
+        potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM_BYTES, s_main>>>(A, W, ld, jb, logdet_blocks, j, dinfo, use_abort ? 1 : 0);
         CUDA_CHECK(cudaGetLastError());
         const int rem = nb - j - 1;
         if (rem == 0) break;
         // panel TRSM as GEMM with the inverted diagonal block: A[i, j] <- A[i, j] * Dinv_j^T  (in place)
-        gemm(0, mapA, A, mapW, W, rect_args(A, EPI_SET, jb + BLK, jb, 2 * rem, 1, jb, jb + BLK), s_main, false);
+        gemm(0, mapA, A, mapW, W, chol_gemm(rect_args(A, EPI_SET, jb + BLK, jb, 2 * rem, 1, jb, jb + BLK)), s_main, false);
         const int ncol = J1 - (j + 1);  // panels of this outer block still to be factored
-        if (ncol > 0) gemm(0, mapA, A, mapA, A, trap_args(jb + BLK, 2 * rem, ncol, jb, jb + BLK), s_main, false);
+        if (ncol > 0) gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(jb + BLK, 2 * rem, ncol, jb, jb + BLK)), s_main, false);
       }
       const int rem = nb - J1;  // panels after this outer block
       if (rem <= 0) break;
@@ -528,10 +775,10 @@ struct Engine {
         CUDA_CHECK(cudaEventRecord(ev_panel[J0], s_main));
         if (last_upd >= 0) CUDA_CHECK(cudaStreamWaitEvent(s_main, ev_upd[last_upd], 0));
         // look-ahead: the next outer block's columns first, on the factorisation stream ...
-        gemm(0, mapA, A, mapA, A, trap_args(c1, 2 * rem, OB, c0, c1), s_main, false);
+        gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1, 2 * rem, OB, c0, c1)), s_main, false);
         // ... the rest of the trailing matrix on the low-priority stream
         CUDA_CHECK(cudaStreamWaitEvent(s_upd, ev_panel[J0], 0));
-        gemm(0, mapA, A, mapA, A, trap_args(c1 + OB * BLK, 2 * (rem - OB), rem - OB, c0, c1), s_upd, false);
+        gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1 + OB * BLK, 2 * (rem - OB), rem - OB, c0, c1)), s_upd, false);
         CUDA_CHECK(cudaEventRecord(ev_upd[J0], s_upd));
         last_upd = J0;
       } else {
@@ -539,10 +786,90 @@ struct Engine {
           CUDA_CHECK(cudaStreamWaitEvent(s_main, ev_upd[last_upd], 0));
           last_upd = -1;
         }
-        gemm(0, mapA, A, mapA, A, trap_args(c1, 2 * rem, rem, c0, c1), s_main, false);
+        gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1, 2 * rem, rem, c0, c1)), s_main, false);
       }
     }
     if (last_upd >= 0) CUDA_CHECK(cudaStreamWaitEvent(s_main, ev_upd[last_upd], 0));
+  }
+
+  // ---- block extension of the kept factor (f3) ----------------------------------------------------------------
+  // LinearAlgebra::update_cholCov + chol_block (LinearAlgebra.cpp:206-299) for populate_Model's update_eligible
+  // case: with o = kept rows, u = appended rows,
+  //     L_oo = kept factor,   L_uo = C_uo L_oo^-T,   L_uu = safe_chol_lower(C_uu - L_uo L_uo^T),
+  // the jitter ladder and the rcond test acting on the Schur complement only; if that ladder is exhausted the
+  // reference falls back to a from-scratch safe_chol_lower(C) (:287-293) -- this returns false and eval() does that.
+  // On the device the split is moved down to the last whole 128-panel boundary c0 <= o: rows [c0, o) of the kept
+  // factor are re-derived (their diagonal carries the jitter the kept factor was accepted with), which leaves
+  // L_oo unchanged up to rounding and lets every step run on whole tiles:
+  //   1. covariance rows >= c0 (cov_build, partial)
+  //   2. row-block solve against the kept panels, right-looking so that every step fills the machine even when few
+  //      rows are appended:  A[c0.., k] <- A[c0.., k] Dinv_k^T ;  A[c0.., k+1..] -= A[c0.., k] A[k+1.., k]^T
+  //   3. Schur complement (one SYRK, k = c0)      4. cholesky(Jstart = c0 / 128).
+  bool factor_update(double alpha, double inv_sigma2, lkgpu_out* out, float& ms_cov, float& ms_chol, float& ms_rcond,
+                     double& rc2_out, int& inc_out, double& diag_out) {
+    const int no = keep_n;
+    const int pb = no / BLK, c0 = pb * BLK, t0 = c0 / PT;
+    const int mrows = 2 * (nb - pb);  // 64-row tiles below c0
+    float t;
+    CUDA_CHECK(cudaEventRecord(ev_t[1], s_main));
+    cov_build(A, alpha, inv_sigma2, 0.0, s_main, t0, false, no, keep_diag_add);
+    CUDA_CHECK(cudaEventRecord(ev_t[2], s_main));
+    for (int k = 0; k < pb; ++k) {
+      const int kb = k * BLK;
+      gemm(0, mapA, A, mapW, W, rect_args(A, EPI_SET, c0, kb, mrows, 1, kb, kb + BLK), s_main, false);
+      if (k + 1 < pb)
+        gemm(0, mapA, A, mapA, A, rect_args(A, EPI_SUB, c0, kb + BLK, mrows, pb - k - 1, kb, kb + BLK), s_main, false);
+    }
+    CUDA_CHECK(cudaEventRecord(ev_t[3], s_main));
+    CUDA_CHECK(cudaStreamSynchronize(s_main));
+    cudaEventElapsedTime(&t, ev_t[1], ev_t[2]); ms_cov += t;
+    cudaEventElapsedTime(&t, ev_t[2], ev_t[3]); ms_chol += t;
+    double diag_add = 0.0;
+    int inc = 0;
+    const int nu = n - no;
+    while (true) {
+      CUDA_CHECK(cudaEventRecord(ev_t[1], s_main));
+      if (inc > 0) cov_build(A, alpha, inv_sigma2, diag_add, s_main, t0, true, no, keep_diag_add);
+      CUDA_CHECK(cudaEventRecord(ev_t[2], s_main));
+      if (pb > 0) gemm(0, mapA, A, mapA, A, trap_args(c0, mrows, nb - pb, 0, c0), s_main, false);
+      cholesky(pb);
+      CUDA_CHECK(cudaEventRecord(ev_t[3], s_main));
+      // info + ||L_uu||_1
+      const double* Luu = A + (long long)no * ld + no;
+      launches += 2;
+      tri_colsum_abs_kernel<<<(nu * 32 + 255) / 256, 256, 0, s_main>>>(Luu, ld, nu, dcolsum);
+      vec_max_kernel<<<1, 256, 0, s_main>>>(dcolsum, nu, dscal + SC_NORML);
+      CUDA_CHECK(cudaMemcpyAsync(hpin, dscal + SC_NORML, 8, cudaMemcpyDeviceToHost, s_main));
+      CUDA_CHECK(cudaMemcpyAsync(hpin + 2, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s_main));
+      CUDA_CHECK(cudaStreamSynchronize(s_main));
+      cudaEventElapsedTime(&t, ev_t[1], ev_t[2]); ms_cov += t;
+      cudaEventElapsedTime(&t, ev_t[2], ev_t[3]); ms_chol += t;
+      const double normL = hpin[0];
+      int info;
+      memcpy(&info, hpin + 2, sizeof(int));
+      const bool ok = (info == 0) && std::isfinite(normL);
+      bool wrong_rcond = rcond_check;
+      double rc2 = NAN;
+      if (ok && rcond_check) {
+        CUDA_CHECK(cudaEventRecord(ev_t[5], s_main));
+        const double rc = rcond_estimate(normL, no);  // dtrcon on L_uu
+        rc2 = rc * rc;
+        wrong_rcond = rc2 < min_rcond;
+        CUDA_CHECK(cudaEventRecord(ev_t[6], s_main));
+        CUDA_CHECK(cudaStreamSynchronize(s_main));
+        cudaEventElapsedTime(&t, ev_t[5], ev_t[6]); ms_rcond += t;
+      }
+      if (!ok || wrong_rcond) {
+        if (inc > max_inc || num_nugget <= 0.0) return false;  // chol_block's catch: factor C from scratch
+        diag_add += num_nugget * std::pow(10.0, inc);
+        ++inc;
+        continue;
+      }
+      rc2_out = rc2;
+      inc_out = inc;
+      diag_out = diag_add;
+      return true;
+    }
   }
 
   // ---- TRTRI: W <- L^-1 (lower), V used as scratch (a4) ----
@@ -585,11 +912,12 @@ struct Engine {
   // ---- triangular sweeps (a5) ----
   template <bool BWD>
   void solve_wave(double* B, int nrhs) {
-    const int grid = std::min(nb, sm_count);
+    int grid = std::min(nb, sm_count);
+    if (wave_grid_cap > 0) grid = std::min(grid, wave_grid_cap);
     for (int q0 = 0; q0 < nrhs; q0 += WAVE_MAX_RHS) {
       const int nq = std::min(WAVE_MAX_RHS, nrhs - q0);
       double* Bq = B + (long long)q0 * N;
-      CUDA_CHECK(cudaMemsetAsync(wave_ctl, 0, (size_t)(nb + 1) * sizeof(int), s_main));
+      dev_zero_ints(wave_ctl, nb + 1);
       ++launches;
       const CUtensorMap& mL = BWD ? mapA.wb : mapA.wf;
       const CUtensorMap& mW = BWD ? mapW.wb : mapW.wf;
@@ -605,12 +933,21 @@ struct Engine {
     }
   }
   // ---- triangular sweeps (a5): one persistent wavefront kernel per sweep (trsv_wave.cuh) ----
+  // With ONE handle on the device the persistent wavefront kernel runs (3 sweeps in 2.3 ms at n = 20000).  With
+  // several handles evaluating concurrently (multistart rows in flight, BASELINE cfg 5) it does not: measured on
+  // B200, ~1.5 % of its sweeps then return a wrong block -- even with a single CTA, i.e. without any inter-CTA
+  // traffic, and with every producer of its TMA operands fenced -- while the launch-chain kernels below, which read
+  // L through ordinary loads, never did (0 of 1080 evaluations).  Until that is understood, concurrent handles
+  // take the launch chain (n <= 8192 there: 40-64 short launches per sweep).  LKGPU_WAVE_ALWAYS=1 overrides.
+  bool sweeps_by_launch_chain() const {
+    return use_step_trsv || (!wave_always && g_live_handles[device & 63].load() > 1);
+  }
   void solve_fwd(double* B, int nrhs) {
-    if (use_step_trsv) return solve_fwd_steps(B, nrhs);
+    if (sweeps_by_launch_chain()) return solve_fwd_steps(B, nrhs);
     solve_wave<false>(B, nrhs);
   }
   void solve_bwd(double* B, int nrhs) {
-    if (use_step_trsv) return solve_bwd_steps(B, nrhs);
+    if (sweeps_by_launch_chain()) return solve_bwd_steps(B, nrhs);
     solve_wave<true>(B, nrhs);
   }
   // launch-chain variant (one kernel per 128-row step), kept for fault localisation: LKGPU_STEP_TRSV=1
@@ -648,21 +985,24 @@ struct Engine {
 
   // dtrcon('1','L','N') restated: Higham/Hager estimator dlacn2 driven from the host,
   // triangular solves on the device (reference: arma::rcond -> dtrcon, auxlib_meat.hpp:6777-6800).
-  double rcond_estimate(double anorm) {
+  // r0 > 0: the estimate is for the trailing block L[r0.., r0..] (chol_block's L_uu): its solves are sweeps of
+  // the whole factor on right-hand sides that are zero above r0, read back below r0.
+  double rcond_estimate(double anorm, int r0 = 0) {
     if (!(anorm > 0.0)) return 0.0;
     const int itmax = 5;
+    const int n = this->n - r0;  // order of the block (shadows the member on purpose)
     std::vector<double> x(n), v(n);
     std::vector<int> isgn(n);
     auto dev_solve = [&](bool transpose) {
-      // padded tail stays zero
-      memcpy(hpin, x.data(), (size_t)n * 8);
-      for (int i = n; i < N; ++i) hpin[i] = 0.0;
+      // rows above r0 and the padded tail are zero
+      for (int i = 0; i < N; ++i) hpin[i] = 0.0;
+      memcpy(hpin + r0, x.data(), (size_t)n * 8);
       CUDA_CHECK(cudaMemcpyAsync(Tv, hpin, (size_t)N * 8, cudaMemcpyHostToDevice, s_main));
       if (transpose) solve_bwd(Tv, 1);
       else solve_fwd(Tv, 1);
       CUDA_CHECK(cudaMemcpyAsync(hpin, Tv, (size_t)N * 8, cudaMemcpyDeviceToHost, s_main));
       CUDA_CHECK(cudaStreamSynchronize(s_main));
-      memcpy(x.data(), hpin, (size_t)n * 8);
+      memcpy(x.data(), hpin + r0, (size_t)n * 8);
     };
     auto dasum = [&](const std::vector<double>& a) {
       double s = 0;
@@ -743,6 +1083,24 @@ struct Engine {
     return (1.0 / anorm) / est;
   }
 
+  void dev_zero(double* p_, long long count) {
+    if (count <= 0) return;
+    ++launches;
+    fill_zero_kernel<<<(unsigned)std::min<long long>((count + 255) / 256, 8LL * sm_count), 256, 0, s_main>>>(p_, count);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  void dev_copy(double* dst, const double* src, long long count) {
+    if (count <= 0) return;
+    ++launches;
+    copy_kernel<<<(unsigned)std::min<long long>((count + 255) / 256, 8LL * sm_count), 256, 0, s_main>>>(dst, src, count);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  void dev_zero_ints(int* p_, int count) {
+    ++launches;
+    zero_ints_kernel<<<(count + 255) / 256, 256, 0, s_main>>>(p_, count);
+    CUDA_CHECK(cudaGetLastError());
+  }
+
   void tic(int idx) { CUDA_CHECK(cudaEventRecord(ev_t[idx], s_main)); }
 
   // deterministic sum of squares of a vector (n rows) into dscal[slot]
@@ -803,16 +1161,29 @@ struct Engine {
     last_alpha = alpha;
     last_inv_sigma2 = inv_sigma2;
     have_model = have_W = have_V = have_x = have_loo = false;
+    live_is_committed = false;
     memset(out->stage_ms, 0, sizeof(out->stage_ms));
     const bool need_inverse = want_grad || objective == LKGPU_OBJ_LOO;
 
     tic(0);
-    // ---- safe_chol_lower (LinearAlgebra.cpp:43-98): jitter ladder driven from the host ----
     double diag_add = 0.0;
     int inc = 0;
     double rc2 = 0.0;
     float ms_cov = 0, ms_chol = 0, ms_rcond = 0, ms_trtri = 0;
-    while (true) {
+    // ---- populate_Model's update_eligible (Kriging.cpp:170-188): same theta / extra as the kept factor and more
+    //      rows than it has -> block extension; anything else (or an exhausted ladder there) -> from scratch ----
+    bool updated = false;
+    last_was_update = last_mixed_jitter = false;
+    if (keep_n > 0) {
+      const bool eligible = keep_n < n && (int)keep_theta.size() == d && std::equal(theta, theta + d, keep_theta.begin()) &&
+                            alpha == keep_alpha && inv_sigma2 == keep_inv_sigma2;
+      if (eligible) updated = factor_update(alpha, inv_sigma2, out, ms_cov, ms_chol, ms_rcond, rc2, inc, diag_add);
+      last_was_update = updated;
+      last_mixed_jitter = updated && diag_add != keep_diag_add;
+      keep_n = 0;  // the kept factor is consumed (or overwritten) by this evaluation
+    }
+    // ---- safe_chol_lower (LinearAlgebra.cpp:43-98): jitter ladder driven from the host ----
+    while (!updated) {
       have_W = false;
       CUDA_CHECK(cudaEventRecord(ev_t[1], s_main));
       cov_build(A, alpha, inv_sigma2, diag_add, s_main);
@@ -912,11 +1283,11 @@ struct Engine {
       launches += 3;
       gram_partial_kernel<<<chunks, 256, 0, s_main>>>(Bv, N, n, p + 1, dpartial);
       gls_final_kernel<<<1, 256, ((p + 1) * (p + 1) + p) * 8, s_main>>>(dpartial, chunks, p, dRstar, dbeta, dinfo + 1);
-      CUDA_CHECK(cudaMemsetAsync(Ev, 0, (size_t)N * 8, s_main));
+      dev_zero(Ev, N);
       residual_kernel<<<(n + 255) / 256, 256, 0, s_main>>>(dy, dF, n, n, p, dbeta, Ev);
       solve_fwd(Ev, 1);
       sum_sq(Ev, SC_SSE);
-      CUDA_CHECK(cudaMemcpyAsync(Xv, Ev, (size_t)N * 8, cudaMemcpyDeviceToDevice, s_main));
+      dev_copy(Xv, Ev, N);
       solve_bwd(Xv, 1);
       have_x = true;
     }
@@ -1227,6 +1598,32 @@ int lkgpu_set_data(void* handle, const double* X, const double* y, const double*
   CUDA_CHECK(cudaSetDevice(e->device));
   e->set_data(X, y, F, noise);
   LK_CATCH
+}
+
+int lkgpu_append_data(void* handle, int n_u, const double* X_u, const double* y_u, const double* F_u,
+                      const double* noise_u) {
+  LK_TRY
+  if (!handle || !X_u || !y_u || !F_u) throw LkError{"lkgpu_append_data: null argument"};
+  static_cast<Engine*>(handle)->append(n_u, X_u, y_u, F_u, noise_u);
+  LK_CATCH
+}
+
+int lkgpu_commit_model(void* handle) {
+  LK_TRY
+  if (!handle) throw LkError{"null handle"};
+  static_cast<Engine*>(handle)->commit();
+  LK_CATCH
+}
+
+int lkgpu_restore_model(void* handle) {
+  LK_TRY
+  if (!handle) throw LkError{"null handle"};
+  static_cast<Engine*>(handle)->restore();
+  LK_CATCH
+}
+
+int lkgpu_last_eval_was_update(void* handle) {
+  return handle ? (static_cast<Engine*>(handle)->last_was_update ? 1 : 0) : 0;
 }
 
 int lkgpu_theta_bounds(void* handle, double lower_factor, double upper_factor, int heuristic, double* lower,

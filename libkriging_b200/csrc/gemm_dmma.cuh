@@ -58,6 +58,10 @@ struct GemmArgs {
   // SCHED_RECT: tiles (tm, tn), tm fastest; SCHED_TRAP: lower trapezoid tm >= 2*tn of a square region
   int row0, col0, mt, nt;
   int k_begin, k_end;
+  // optional: when *abort_flag != 0 at kernel start the launch is a no-op.  Set for the launches of a Cholesky
+  // attempt: once a panel has found a non-positive pivot (info != 0) the attempt is discarded by safe_chol_lower's
+  // ladder (LinearAlgebra.cpp:66-90), so the rest of its trailing updates is skipped.
+  const int* abort_flag;
 };
 
 __device__ __forceinline__ TileDesc gemm_get_tile(const GemmArgs& a, int id) {
@@ -167,6 +171,13 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (args.abort_flag != nullptr) {
+    // one read per CTA, so that the whole CTA takes the same branch even if the flag is raised right now
+    __shared__ int s_abort;
+    if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(args.abort_flag);
+    __syncthreads();
+    if (s_abort != 0) return;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GSTAGES; ++s) {
@@ -328,6 +339,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constan
         }
       }
     }
+    fence_writes_for_tma();  // C is an operand of later TMA-fed kernels (see common.cuh)
   }
 }
 
@@ -338,6 +350,7 @@ __global__ void gemm_simple_kernel(const double* __restrict__ Mbuf, long long ld
                                    long long ldn, const GemmArgs args) {
   // blockDim.x must be 256: each thread owns 32 elements; sums are formed before any store so that the
   // in-place panel TRSM (C aliases the M-side operand) is safe, exactly as in the DMMA kernel.
+  if (args.abort_flag != nullptr && *reinterpret_cast<const volatile int*>(args.abort_flag) != 0) return;
   for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
     TileDesc td = gemm_get_tile(args, tile);
     double sums[32];

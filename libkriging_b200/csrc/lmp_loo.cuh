@@ -112,6 +112,7 @@ scaled_bm_kernel(const double* __restrict__ V, long long ld, const double* __res
       for (int q = 0; q < p; ++q) v -= U[(long long)q * ldu + i] * U[(long long)q * ldu + j];
     Q[(long long)j * ld + i] = sc * v;
   }
+  fence_writes_for_tma();  // Q is a TMA operand of the LOO-gradient product
 }
 
 // out = Vsym * w - U (U^T w) for a lower-block-triangle-stored symmetric V: one warp per row pair sweep.
@@ -263,7 +264,7 @@ void Engine::lmp_loo_prepare(int objective, int& pdim) {
   pdim = p;
   const int q = p + 1;
   // [Rinv_X | yt_Rinv] = L^T \ [Fstar | ystar]
-  CUDA_CHECK(cudaMemcpyAsync(Zv, Bv, (size_t)N * q * 8, cudaMemcpyDeviceToDevice, s_main));
+  dev_copy(Zv, Bv, (long long)N * q);
   solve_bwd(Zv, q);
   // H = [F | y]^T [Rinv_X | yt_Rinv]   (q x q)
   const int chunks = (n + GRAM_CHUNK - 1) / GRAM_CHUNK;
@@ -304,8 +305,8 @@ void Engine::lmp_loo_prepare(int objective, int& pdim) {
   memcpy(hpin, T.data(), (size_t)p * p * 8);
   memcpy(hpin + (size_t)p * p, w.data(), (size_t)p * 8);
   CUDA_CHECK(cudaMemcpyAsync(dsmall, hpin, ((size_t)p * p + p) * 8, cudaMemcpyHostToDevice, s_main));
-  CUDA_CHECK(cudaMemsetAsync(Uv, 0, (size_t)N * p * 8, s_main));
-  CUDA_CHECK(cudaMemsetAsync(Qv, 0, (size_t)N * 8, s_main));
+  dev_zero(Uv, (long long)N * p);
+  dev_zero(Qv, N);
   launches += 1;
   right_mult_small_kernel<<<(n + 255) / 256, 256, 0, s_main>>>(Zv, N, dsmall, p, n, Uv, N, Zv + (size_t)N * p,
                                                                dsmall + (size_t)p * p, Qv);
@@ -332,7 +333,7 @@ void Engine::loo_finish(int want_grad) {
   // v = Bm (e.s)
   launches += 3;
   symv_lower_kernel<<<(n * 32 + 255) / 256, 256, 0, s_main>>>(V, ld, dEs, n, Tv);
-  CUDA_CHECK(cudaMemsetAsync(Tv + n, 0, (size_t)(N - n) * 8, s_main));
+  dev_zero(Tv + n, N - n);
   cross_partial_kernel<<<(n + GRAM_CHUNK - 1) / GRAM_CHUNK, 256, 0, s_main>>>(Uv, N, p, dEs, N, 1, n, dpartial);
   sum_partials_kernel<<<(p + 63) / 64, 64, 0, s_main>>>(dpartial, (n + GRAM_CHUNK - 1) / GRAM_CHUNK, p, p, dsmall);
   launches += 1;

@@ -60,7 +60,7 @@ __device__ __forceinline__ void potf2_invert_diag(const double* __restrict__ Ld,
 
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, int jb, double* __restrict__ logdet_blocks,
-                 int blk_index, int* __restrict__ info) {
+                 int blk_index, int* __restrict__ info, int check_abort) {
   extern __shared__ double sm[];
   double* As = sm;                     // 128*128
   double* Xb = sm + 128 * 128;         // 10 blocks of 32x32: Xb[blk][c*32 + r] = X[32i + r, 32j + c]
@@ -71,6 +71,13 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   double* Ablk = A + (long long)jb * ld + jb;
+  // an earlier panel of this attempt already failed: the attempt is discarded, skip the rest of it
+  if (check_abort) {
+    __shared__ int s_abort;
+    if (tid == 0) s_abort = *reinterpret_cast<const volatile int*>(info);
+    __syncthreads();
+    if (s_abort != 0) return;
+  }
 
   for (int idx = tid; idx < 128 * 64; idx += POTF2_THREADS) {
     const int c = idx >> 6, r2 = (idx & 63) * 2;
@@ -227,6 +234,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
     if (i >= j) v = *reinterpret_cast<const double2*>(Xb + potf2_blk(i, j) * 1024 + (c & 31) * 32 + (r2 & 31));
     *reinterpret_cast<double2*>(Wblk + (long long)c * ld + r2) = v;
   }
+  fence_writes_for_tma();  // both blocks are TMA operands of the panel TRSM, TRTRI and the sweeps
 }
 
 }  // namespace lk

@@ -40,6 +40,15 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// strong (gpu-scope) accesses for the right-hand-side blocks that travel between CTAs inside one sweep
+__device__ __forceinline__ double ld_relaxed_gpu_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_f64(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 __device__ __forceinline__ void bar_sync_compute() {
   asm volatile("bar.sync 1, %0;" ::"n"(WAVE_COMPUTE_THREADS) : "memory");
 }
@@ -119,7 +128,7 @@ trsv_wave_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constan
     const int r = tid & 127, h = tid >> 7;
     double acc[NQ];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) acc[q] = (h == 0 && q < nrhs) ? B[q * ldb + ib + r] : 0.0;
+    for (int q = 0; q < NQ; ++q) acc[q] = (h == 0 && q < nrhs) ? ld_relaxed_gpu_f64(B + q * ldb + ib + r) : 0.0;
 
     for (int tq = 0; tq < ntiles; ++tq) {
       const bool diag = (tq == ntiles - 1);
@@ -132,7 +141,7 @@ trsv_wave_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constan
         bar_sync_compute();
         if (tid < 128) {
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) vec[q * 128 + tid] = (q < nrhs) ? __ldcg(B + q * ldb + j * 128 + tid) : 0.0;
+          for (int q = 0; q < NQ; ++q) vec[q * 128 + tid] = (q < nrhs) ? ld_relaxed_gpu_f64(B + q * ldb + j * 128 + tid) : 0.0;
         }
         bar_sync_compute();
       } else {
@@ -193,7 +202,7 @@ trsv_wave_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constan
     if (h == 0) {
 #pragma unroll
       for (int q = 0; q < NQ; ++q)
-        if (q < nrhs) __stcg(B + q * ldb + ib + r, part[q * 128 + r] + part[(NQ + q) * 128 + r]);
+        if (q < nrhs) st_relaxed_gpu_f64(B + q * ldb + ib + r, part[q * 128 + r] + part[(NQ + q) * 128 + r]);
       __threadfence();
     }
     bar_sync_compute();

@@ -26,7 +26,7 @@ def build() -> bool:
 
 def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL", regmodel="constant", normalize=False,
         mode="eval", optim="none", theta=None, gamma=None, grad=True, sigma2=None, est_sigma2=None, nugget=None,
-        est_nugget=None, Xn=None, device=0, timeout=None):
+        est_nugget=None, Xn=None, device=0, timeout=None, update=None):
     """Run lkgpu::Kriging on (X, y): mode='fit' (optim=BFGS[#]) or 'eval' (objective value / gradient at theta or
     gamma).  Returns the driver's JSON (theta, beta, sigma2, nugget, objective_at_fit, pred_mean, pred_sd, ...)."""
     if not available():
@@ -55,6 +55,15 @@ def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL",
             Xn = np.asfortranarray(Xn, dtype=np.float64)
             cfg["m"] = Xn.shape[0]
             Xn.T.ravel().tofile(os.path.join(wd, "Xn.bin"))
+        if update is not None:
+            # update = dict(X=..., y=..., refit=bool, noise=...): lkgpu::Kriging::update after the fit
+            Xu = np.asfortranarray(update["X"], dtype=np.float64)
+            cfg["update_n"] = Xu.shape[0]
+            cfg["update_refit"] = int(bool(update.get("refit", False)))
+            Xu.T.ravel().tofile(os.path.join(wd, "Xu.bin"))
+            np.ascontiguousarray(update["y"], dtype=np.float64).tofile(os.path.join(wd, "yu.bin"))
+            if update.get("noise") is not None:
+                np.ascontiguousarray(update["noise"], dtype=np.float64).tofile(os.path.join(wd, "noiseu.bin"))
         with open(os.path.join(wd, "cfg.txt"), "w") as f:
             for k, v in cfg.items():
                 f.write(f"{k}={v}\n")

@@ -81,6 +81,22 @@ int main(int argc, char** argv) {
       js << "\"value\": " << std::scientific << std::get<0>(res) << ", ";
       jvec(js, "grad", std::get<1>(res)); js << ", ";
     }
+    // Kriging::update with n_u further observations (same protocol as oracle/ref_driver.cpp)
+    const int n_u = geti("update_n", 0);
+    if (n_u > 0) {
+      arma::mat Xu(read_bin(wd + "/Xu.bin", (size_t)n_u * d).data(), n_u, d);
+      arma::vec yu(read_bin(wd + "/yu.bin", n_u).data(), n_u);
+      const bool refit = geti("update_refit", 0) != 0;
+      const double t1 = now_s();
+      if (nm == NM::Heterogeneous) {
+        arma::vec nu(read_bin(wd + "/noiseu.bin", n_u).data(), n_u);
+        k.update(yu, nu, Xu, refit);
+      } else {
+        k.update(yu, Xu, refit);
+      }
+      js << "\"update_s\": " << (now_s() - t1) << ", \"used_block_extension\": "
+         << (k.last_update_used_block_extension() ? 1 : 0) << ", ";
+    }
     js.precision(17);
     jvec(js, "theta", k.theta()); js << ", ";
     jvec(js, "beta", k.beta()); js << ", ";
@@ -89,6 +105,7 @@ int main(int argc, char** argv) {
       const double ll = objective == "LOO" ? k.leaveOneOut() : (objective == "LMP" ? k.logMargPost() : k.logLikelihood());
       js << "\"objective_at_fit\": " << ll << ", ";
     }
+    if (mode == "fit" || n_u > 0) js << "\"LL_at_model\": " << std::scientific << k.logLikelihood() << ", ";
     if (exists(wd + "/Xn.bin")) {
       const int m = geti("m", 0);
       arma::mat Xn(read_bin(wd + "/Xn.bin", (size_t)m * d).data(), m, d);

@@ -191,6 +191,7 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
     throw std::invalid_argument("LMP objective not supported for Heterogeneous noise mode");
   m_objective = objective_name;
   m_regmodel = regmodel;
+  m_optim = optim;
 
   // ---- fit_setup_impl (KrigingImpl.cpp:764-841) ----
   m_normalize = normalize;
@@ -246,6 +247,7 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
     if (!theta0.has_value())
       throw std::runtime_error("Theta should be given (1x" + std::to_string(d) + ") matrix, when optim=none");
     m_theta = theta0->row(0).t();
+    m_est_theta = false;
     double sigma2 = -1.0;
     m_est_sigma2 = prm.is_sigma2_estim;
     if (prm.sigma2.has_value()) sigma2 = *prm.sigma2 / scaleY2;
@@ -263,6 +265,7 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
     double SSE;
     arma::vec betahat;
     model_scalars(m_theta, extra, &SSE, &betahat);
+    check(lkgpu_commit_model(m_h));
     m_commit_extra = extra;
     m_is_empty = false;
     if (m_est_beta) m_beta = betahat;
@@ -446,6 +449,8 @@ void Kriging::commit(const arma::vec& best_gamma) {
   double SSE;
   arma::vec betahat;
   model_scalars(m_theta, commit_extra, &SSE, &betahat);
+  check(lkgpu_commit_model(m_h));
+  m_est_theta = true;
   m_commit_extra = commit_extra;
   m_is_empty = false;
   if (m_est_beta) m_beta = betahat;
@@ -474,9 +479,144 @@ void Kriging::commit(const arma::vec& best_gamma) {
 
 void Kriging::need_model() {
   if (m_is_empty || !m_h) throw std::runtime_error("Kriging model is not fitted");
+  // make sure the live model on the device is the committed one (objective calls may have replaced it)
+  check(lkgpu_restore_model(m_h));
+  m_have_scalars = false;
+}
+
+// ---- update (reference src/lib/Kriging.cpp:2425-2660) ----
+void Kriging::update(const arma::vec& y_u, const arma::vec& noise_u, const arma::mat& X_u, bool refit) {
+  if (m_noise_model != NoiseModel::Heterogeneous)
+    throw std::runtime_error("update(y, noise, X) requires NoiseModel::Heterogeneous");
+  if (m_is_empty || !m_h) throw std::runtime_error("Kriging model is not fitted");
+  if (y_u.n_elem != X_u.n_rows)
+    throw std::runtime_error("Dimension of new data should be the same:\n X: (" + std::to_string(X_u.n_rows) + "x" +
+                             std::to_string(X_u.n_cols) + "), y: (" + std::to_string(y_u.n_elem) + ")");
+  if (noise_u.n_elem != y_u.n_elem) throw std::runtime_error("noise_u must have the same length as y_u");
+  // a new fit on the joined, de-normalised data, started from the current parameters (:2645-2658)
+  const arma::vec y_all = arma::join_cols(m_y * m_scaleY + m_centerY, y_u);
+  const arma::vec noise_all = arma::join_cols(m_noise * m_scaleY * m_scaleY, noise_u);
+  arma::mat Xd = m_X;
+  Xd.each_row() %= m_scaleX;
+  Xd.each_row() += m_centerX;
+  const arma::mat X_all = arma::join_cols(Xd, X_u);
+  Parameters prm;
+  prm.sigma2 = m_sigma2 * m_scaleY * m_scaleY;
+  prm.is_sigma2_estim = m_est_sigma2;
+  prm.theta = arma::mat(m_theta.t() % m_scaleX);
+  prm.is_theta_estim = m_est_theta;
+  if (!m_est_beta) prm.beta = m_beta * m_scaleY;
+  prm.is_beta_estim = m_est_beta;
+  const std::string optim = refit ? m_optim : "none", objective_name = m_objective, regmodel = m_regmodel;
+  fit_impl(y_all, &noise_all, X_all, regmodel, m_normalize, optim, objective_name, prm);
+}
+
+void Kriging::update(const arma::vec& y_u, const arma::mat& X_u, bool refit) {
+  if (m_is_empty || !m_h) throw std::runtime_error("Kriging model is not fitted");
+  const arma::uword d = m_X.n_cols;
+  if (y_u.n_elem != X_u.n_rows)
+    throw std::runtime_error("Dimension of new data should be the same:\n X: (" + std::to_string(X_u.n_rows) + "x" +
+                             std::to_string(X_u.n_cols) + "), y: (" + std::to_string(y_u.n_elem) + ")");
+  if (X_u.n_cols != d)
+    throw std::runtime_error("Dimension of new data should be the same:\n X: (...x" + std::to_string(d) +
+                             "), new X: (...x" + std::to_string(X_u.n_cols) + ")");
+  if (m_noise_model == NoiseModel::Heterogeneous)
+    throw std::runtime_error("update(y, noise, X) requires a noise vector for NoiseModel::Heterogeneous");
+  const NoiseModel nm = m_noise_model;
+  m_used_block = false;
+  if (refit && m_optim != "none" && nm == NoiseModel::Nugget) {
+    // Nugget refit: a new fit on the de-normalised joined data (:2443-2468)
+    const arma::vec y_all = arma::join_cols(m_y * m_scaleY + m_centerY, y_u);
+    arma::mat Xd = m_X;
+    Xd.each_row() %= m_scaleX;
+    Xd.each_row() += m_centerX;
+    const arma::mat X_all = arma::join_cols(Xd, X_u);
+    Parameters prm;
+    if (!(m_est_beta && m_est_nugget && m_est_sigma2 && m_est_theta)) {
+      prm.sigma2 = m_sigma2 * m_scaleY * m_scaleY;
+      prm.is_sigma2_estim = m_est_sigma2;
+      prm.theta = arma::mat(m_theta.t() % m_scaleX);
+      prm.is_theta_estim = m_est_theta;
+      prm.nugget = m_nugget * m_scaleY * m_scaleY;
+      prm.is_nugget_estim = m_est_nugget;
+      if (!m_est_beta) {
+        prm.beta = m_beta * m_scaleY;
+        prm.is_beta_estim = false;
+      }
+    }
+    const std::string optim = m_optim, objective_name = m_objective, regmodel = m_regmodel;
+    fit_impl(y_all, nullptr, X_all, regmodel, m_normalize, optim, objective_name, prm);
+    return;
+  }
+
+  // ---- extend the data with the model's own normalisation; the device keeps the committed factor ----
+  need_model();
+  arma::mat Xn_u = X_u;
+  Xn_u.each_row() -= m_centerX;
+  Xn_u.each_row() /= m_scaleX;
+  const arma::vec yn_u = (y_u - m_centerY) / m_scaleY;
+  const arma::mat F_u = regression_model_matrix(m_regmodel, Xn_u);
+  check(lkgpu_append_data(m_h, (int)Xn_u.n_rows, Xn_u.memptr(), yn_u.memptr(), F_u.memptr(), nullptr));
+  m_have_scalars = false;
+  m_X = arma::join_cols(m_X, Xn_u);
+  m_y = arma::join_cols(m_y, yn_u);
+  m_F = arma::join_cols(m_F, F_u);
+  const arma::uword n = m_X.n_rows, p = m_F.n_cols;
+  const double extra = nm == NoiseModel::Nugget ? m_alpha : 1.0;
   double SSE;
-  arma::vec b;
-  model_scalars(m_theta, m_commit_extra, &SSE, &b);  // make sure the device holds the committed model
+  arma::vec betahat;
+
+  if (!(refit && m_optim != "none")) {
+    // update_no_refit_impl (KrigingImpl.cpp:576-625): make_Model(m_theta) -- update_eligible -> block extension
+    model_scalars(m_theta, extra, &SSE, &betahat);
+    m_used_block = lkgpu_last_eval_was_update(m_h) != 0;
+    check(lkgpu_commit_model(m_h));
+    m_commit_extra = extra;
+    if (m_est_beta) m_beta = betahat;
+    if (m_est_sigma2) m_sigma2 = SSE / n;
+    push_params();
+    return;
+  }
+
+  // ---- warm restart (:2470-2623): a single L-BFGS-B run from the current theta on the extended data ----
+  const int obj = objective_id(m_objective);
+  arma::vec theta_lower(d), theta_upper(d);
+  check(lkgpu_theta_bounds(m_h, config.theta_lower_factor, config.theta_upper_factor,
+                           config.variogram_bounds_heuristic, theta_lower.memptr(), theta_upper.memptr()));
+  arma::vec gamma_start = reparam_to(m_theta);
+  arma::vec gamma_lower = arma::min(gamma_start, reparam_to(theta_lower));
+  arma::vec gamma_upper = arma::max(gamma_start, reparam_to(theta_upper));
+  model_scalars(m_theta, extra, &SSE, &betahat);  // the warm-up populate_Model at m_theta (:2544-2547)
+  m_used_block = lkgpu_last_eval_was_update(m_h) != 0;
+  const double sign = obj == LKGPU_OBJ_LOO ? 1.0 : -1.0;
+  const double nn = (double)n * (double)n;
+  lbfgsb::Optimizer optimizer{(unsigned int)d};
+  optimizer.iprint = -1;
+  optimizer.max_iter = config.max_iteration;
+  optimizer.pgtol = obj == LKGPU_OBJ_LOO ? config.gradient_tolerance / nn : config.gradient_tolerance;
+  optimizer.factr = obj == LKGPU_OBJ_LOO ? config.objective_rel_tolerance / 1e-13 / nn
+                                         : config.objective_rel_tolerance / 1e-13;
+  std::vector<int> bounds_type(d, 2);
+  arma::vec gamma_tmp = gamma_start;
+  optimizer.minimize(
+      [&](const arma::vec& x, arma::vec& grad) -> double {
+        const arma::vec v = reparam_from(x);
+        arma::vec g;
+        const double val = objective(obj, v, &g);
+        grad = sign * reparam_deriv(v, g);
+        return sign * val;
+      },
+      gamma_tmp, gamma_lower.memptr(), gamma_upper.memptr(), bounds_type.data());
+  m_theta = reparam_from(gamma_tmp).head(d);
+  m_est_theta = true;
+  // (the reference commits whatever model the optimiser's last evaluation left in km; here the model at the returned
+  //  point is rebuilt by one value-only evaluation -- the same point unless the line search failed)
+  model_scalars(m_theta, extra, &SSE, &betahat);
+  check(lkgpu_commit_model(m_h));
+  m_commit_extra = extra;
+  if (m_est_beta) m_beta = betahat;
+  if (m_est_sigma2) m_sigma2 = m_objective == "LMP" ? SSE / (double)(n - p) : SSE / n;
+  push_params();
 }
 
 arma::vec Kriging::gamma_full(const arma::vec& theta) const {

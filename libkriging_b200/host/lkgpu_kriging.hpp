@@ -64,6 +64,12 @@ class Kriging {
            bool normalize = false, const std::string& optim = "BFGS", const std::string& objective = "LL",
            const Parameters& parameters = Parameters());
 
+  // Kriging::update (src/lib/Kriging.cpp:2425-2660): block extension of the committed factor (refit = false), warm
+  // restart (refit = true), a new fit for the Nugget refit and for the Heterogeneous overload.
+  void update(const arma::vec& y_u, const arma::mat& X_u, bool refit = true);
+  void update(const arma::vec& y_u, const arma::vec& noise_u, const arma::mat& X_u, bool refit = true);
+  bool last_update_used_block_extension() const { return m_used_block; }
+
   std::tuple<double, arma::vec> logLikelihoodFun(const arma::vec& theta, bool return_grad);
   std::tuple<double, arma::vec> leaveOneOutFun(const arma::vec& theta, bool return_grad);
   std::tuple<double, arma::vec> logMargPostFun(const arma::vec& theta, bool return_grad);
@@ -104,7 +110,8 @@ class Kriging {
   int m_device, m_rank = 0, m_world = 1;
   void* m_h = nullptr;
   bool m_is_empty = true, m_normalize = false;
-  bool m_est_beta = true, m_est_sigma2 = true, m_est_nugget = true;
+  bool m_est_beta = true, m_est_sigma2 = true, m_est_nugget = true, m_est_theta = true, m_used_block = false;
+  std::string m_optim = "BFGS";
   arma::mat m_X, m_F;
   arma::vec m_y, m_noise, m_theta, m_beta;
   arma::rowvec m_centerX, m_scaleX;

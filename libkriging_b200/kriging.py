@@ -38,6 +38,8 @@ class GpuBackend:
         self.info = {}
         self._scalars_key = None
         self._scalars = None
+        # running totals over this handle's objective calls (bench.py reports them for the fit)
+        self.stats = dict(evals=0, jitter_rungs=0, device_ms=0.0)
 
     def set_params(self, est_sigma2, sigma2, est_nugget, nugget, alpha):
         self.engine.set_params(est_sigma2, sigma2, est_nugget, nugget, alpha)
@@ -52,6 +54,10 @@ class GpuBackend:
         val, grad, info = self.engine.objective(name, gamma, want_grad, with_info=True)
         self.info = info
         self._scalars_key = None  # the device now holds the model at gamma
+        st = self.stats
+        st["evals"] += 1
+        st["jitter_rungs"] += int(info["n_jitter"])
+        st["device_ms"] += float(info["stage_ms"]["total"])
         return val, grad
 
     def model_scalars(self, theta, extra):
@@ -64,6 +70,25 @@ class GpuBackend:
 
     def export(self, which):
         return self.engine.export(which)
+
+    def append_data(self, X_u, y_u, F_u, noise_u=None):
+        """Kriging::update, data side: the device keeps the committed factor for a block extension at the same
+        theta (lkgpu_append_data)."""
+        self.engine.append_data(X_u, y_u, F_u, noise_u)
+        self._scalars_key = None
+
+    def commit(self):
+        """The model of the last evaluation becomes the committed one (Kriging.cpp:2156-2173)."""
+        self.engine.commit_model()
+
+    def restore(self):
+        """The committed model becomes the live one again (objective calls at other points replaced it)."""
+        self.engine.restore_model()
+        self._scalars_key = None
+
+    @property
+    def used_block_update(self):
+        return self.engine.last_eval_was_update
 
     def max_handles(self):
         """How many handles of this size fit in 70 % of the device memory that is free now (+ this one)."""
@@ -287,6 +312,7 @@ class Kriging:
             elif nm == "hetero":
                 extra = sigma2 if sigma2 > 0 else self.m_sigma2
             SSE, betahat = be.model_scalars(self.m_theta, extra)
+            be.commit()
             self._commit_extra = extra
             self.m_is_empty = False
             if self.m_est_beta:
@@ -481,6 +507,7 @@ class Kriging:
         extra_param = float(v[d]) if gd > d else 0.0
         commit_extra = extra_param if gd > d else 1.0
         SSE, betahat = be.model_scalars(self.m_theta, commit_extra)
+        be.commit()
         self._commit_extra = commit_extra
         self.m_is_empty = False
         if self.m_est_beta:
@@ -508,6 +535,125 @@ class Kriging:
         self._push_params()
         return self
 
+    # ---- update (reference src/lib/Kriging.cpp:2425-2660) ----
+    def update(self, y_u, X_u, refit=True, noise_u=None):
+        """Kriging::update(y_u, X_u, refit) / update(y_u, noise_u, X_u, refit): add observations to a fitted model.
+
+        * Heterogeneous (noise_u given) and Nugget with refit: a new fit() on the joined, de-normalised data, started
+          from the current parameters (Kriging.cpp:2443-2468, 2635-2658).
+        * refit (NoiseModel::None): warm restart -- one L-BFGS-B run from the current theta on the extended data
+          (:2470-2623).
+        * no refit: the model is extended at the current theta (KrigingImpl::update_no_refit_impl,
+          KrigingImpl.cpp:576-625).
+        In the last two cases the committed factor stays on the device and the first evaluation at the current theta
+        is the block extension of LinearAlgebra::update_cholCov / chol_block (lkgpu_append_data)."""
+        if self.m_is_empty or self._backend is None:
+            raise RuntimeError("Kriging model is not fitted")
+        y_u = np.asarray(y_u, dtype=np.float64).ravel()
+        X_u = np.asarray(X_u, dtype=np.float64)
+        d = self.m_X.shape[1]
+        if X_u.ndim == 1:
+            X_u = X_u.reshape(-1, d)
+        if y_u.size != X_u.shape[0]:
+            raise RuntimeError(f"Dimension of new data should be the same:\n X: ({X_u.shape[0]}x{X_u.shape[1]}), "
+                               f"y: ({y_u.size})")
+        if X_u.shape[1] != d:
+            raise RuntimeError(f"Dimension of new data should be the same:\n X: (...x{d}), new X: (...x{X_u.shape[1]})")
+        nm = self.m_noise_model
+        sY = self.m_scaleY
+        y_all = lambda: np.concatenate([self.m_y * sY + self.m_centerY, y_u])          # noqa: E731
+        X_all = lambda: np.vstack([self.m_X * self.m_scaleX + self.m_centerX, X_u])    # noqa: E731
+        if nm == "hetero":
+            if noise_u is None:
+                raise RuntimeError("update(y, noise, X) requires NoiseModel::Heterogeneous")
+            noise_u = np.asarray(noise_u, dtype=np.float64).ravel()
+            if noise_u.size != y_u.size:
+                raise RuntimeError("noise_u must have the same length as y_u")
+            params = dict(sigma2=self.m_sigma2 * sY * sY, is_sigma2_estim=self.m_est_sigma2,
+                          theta=(self.m_theta * self.m_scaleX)[None, :], is_theta_estim=self.m_est_theta,
+                          beta=None if self.m_est_beta else self.m_beta * sY, is_beta_estim=self.m_est_beta)
+            noise_all = np.concatenate([self.m_noise * sY * sY, noise_u])
+            return self.fit(y_all(), X_all(), self.m_regmodel, self.m_normalize, self.m_optim if refit else "none",
+                            self.m_objective, params, noise=noise_all)
+        if noise_u is not None:
+            raise RuntimeError("update(y, noise, X) requires NoiseModel::Heterogeneous")
+        if refit and self.m_optim != "none" and nm == "nugget":
+            params = {}
+            if not (self.m_est_beta and self.m_est_nugget and self.m_est_sigma2 and self.m_est_theta):
+                params = dict(sigma2=self.m_sigma2 * sY * sY, is_sigma2_estim=self.m_est_sigma2,
+                              theta=(self.m_theta * self.m_scaleX)[None, :], is_theta_estim=self.m_est_theta,
+                              nugget=self.m_nugget * sY * sY, is_nugget_estim=self.m_est_nugget)
+                if not self.m_est_beta:
+                    params.update(beta=self.m_beta * sY, is_beta_estim=False)
+            return self.fit(y_all(), X_all(), self.m_regmodel, self.m_normalize, self.m_optim, self.m_objective, params)
+
+        # ---- extend the data with the model's own normalisation; the device keeps the committed factor ----
+        be = self._backend
+        self._need_model()
+        Xn_u = (X_u - self.m_centerX) / self.m_scaleX
+        yn_u = (y_u - self.m_centerY) / sY
+        F_u = regression_model_matrix(self.m_regmodel, Xn_u)
+        be.append_data(Xn_u, yn_u, F_u)
+        self.m_X = np.asfortranarray(np.vstack([self.m_X, Xn_u]))
+        self.m_y = np.concatenate([self.m_y, yn_u])
+        self.m_F = np.vstack([self.m_F, F_u])
+        n, p = self.m_F.shape
+        extra = self.m_alpha if nm == "nugget" else 1.0
+
+        if not (refit and self.m_optim != "none"):
+            # update_no_refit_impl: make_Model(m_theta) -- update_eligible -> block extension
+            SSE, betahat = be.model_scalars(self.m_theta, extra)
+            be.commit()
+            self._commit_extra = extra
+            if self.m_est_beta:
+                self.m_beta = betahat
+            if self.m_est_sigma2:
+                self.m_sigma2 = SSE / n
+            self._push_params()
+            return self
+
+        # ---- warm restart (Kriging.cpp:2470-2623): a single L-BFGS-B run from the current theta ----
+        cfg = self.config
+        objective = self.m_objective
+        theta_lower, theta_upper = be.theta_bounds(cfg.theta_lower_factor, cfg.theta_upper_factor,
+                                                   cfg.variogram_bounds_heuristic)
+        rp = _optim.Reparam("none", d, cfg.reparametrize)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            gamma_start = rp.to(self.m_theta.copy())
+            gamma_lower = np.minimum(gamma_start, rp.to(theta_lower))
+            gamma_upper = np.maximum(gamma_start, rp.to(theta_upper))
+        be.model_scalars(self.m_theta, extra)  # the warm-up populate_Model at m_theta (:2544-2547): block extension
+        sign = 1.0 if objective == "LOO" else -1.0
+        counter = [0]
+
+        def fg(gamma):
+            counter[0] += 1
+            v = rp.frm(gamma)
+            val, grad = be.objective(objective, v, True)
+            return sign * val, sign * rp.deriv(v, grad)
+
+        if objective == "LOO":
+            pgtol, factr = cfg.gradient_tolerance / (n * n), cfg.objective_rel_tolerance / 1e-13 / (n * n)
+        else:
+            pgtol, factr = cfg.gradient_tolerance, cfg.objective_rel_tolerance / 1e-13
+        r = lbfgsb_minimize(fg, gamma_start, gamma_lower, gamma_upper, max_iter=cfg.max_iteration, pgtol=pgtol,
+                            factr=factr)
+        self.m_theta = rp.frm(r.x)[:d].copy()
+        self.m_est_theta = True
+        # (the reference commits whatever model the optimiser's last evaluation left in km; here the model at the
+        #  returned point is rebuilt by one value-only evaluation -- the same point unless the line search failed)
+        SSE, betahat = be.model_scalars(self.m_theta, extra)
+        be.commit()
+        self._commit_extra = extra
+        if self.m_est_beta:
+            self.m_beta = betahat
+        if self.m_est_sigma2:
+            self.m_sigma2 = SSE / (n - p) if objective == "LMP" else SSE / n
+        self.fit_log = dict(multistart=1, best_start=0, objective=r.f_opt, n_eval=counter[0] + 2,
+                            theta_lower=theta_lower, theta_upper=theta_upper, warm_restart=True)
+        self._push_params()
+        return self
+
     # ---- helpers ----
     def _concurrency(self, n_starts, n):
         """Number of engine handles this process runs concurrently for its multistart rows.  Explicit:
@@ -531,8 +677,8 @@ class Kriging:
     def _need_model(self):
         if self.m_is_empty or self._backend is None:
             raise RuntimeError("Kriging model is not fitted")
-        # make sure the device holds the committed model (objective calls at other thetas may have replaced it)
-        self._backend.model_scalars(self.m_theta, self._commit_extra)
+        # make sure the live model on the device is the committed one (objective calls may have replaced it)
+        self._backend.restore()
 
     def _sigma2_variogram(self):
         """Heterogeneous sigma2 bounds (Kriging.cpp:1784-1797): half the mean squared increment over the pairs

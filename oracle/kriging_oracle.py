@@ -140,6 +140,42 @@ def solve_lower(L, B):
     return x
 
 
+def chol_block(Cm: np.ndarray, Loo: np.ndarray, num: Numerics | None = None):
+    """LinearAlgebra::chol_block (src/lib/LinearAlgebra.cpp:254-299): Cholesky root of C knowing the root Loo of its
+    leading block.  Lou = Loo \\ Cou, Luu = safe_chol_lower(Cuu - Lou' Lou) -- the jitter ladder and the rcond test
+    act on the Schur complement only; if that ladder is exhausted, a from-scratch safe_chol_lower(C) (:287-293).
+    Returns (L, n_jitter, rcond2, used_block)."""
+    n, no = Cm.shape[0], Loo.shape[0]
+    Cou = Cm[:no, no:]
+    Cuu = Cm[no:, no:]
+    L = np.zeros((n, n))
+    L[:no, :no] = Loo
+    Lou = solve_lower(Loo, Cou)
+    L[no:, :no] = Lou.T
+    try:
+        Luu, inc, rc2 = safe_chol_lower(Cuu - Lou.T @ Lou, num)
+    except RuntimeError:
+        Lf, inc, rc2 = safe_chol_lower(Cm, num)
+        return np.tril(Lf), inc, rc2, False
+    L[no:, no:] = Luu
+    return np.tril(L), inc, rc2, True
+
+
+def update_chol_cov(X, theta, kernel, alpha, diag, T_old, R_old, num: Numerics | None = None):
+    """LinearAlgebra::update_cholCov (src/lib/LinearAlgebra.cpp:206-243): R = [R_old, new columns; ...] with the new
+    off-diagonal entries alpha * rho, the diagonal 1 (or `diag`), then chol_block(R, T_old).
+    Returns (R, L, n_jitter, rcond2, used_block)."""
+    no = T_old.shape[0]
+    R = build_R(X, theta, kernel, alpha, diag)
+    R[:no, :no] = R_old
+    if diag is None:
+        np.fill_diagonal(R, 1.0)
+    else:
+        np.fill_diagonal(R, diag)
+    L, inc, rc2, used = chol_block(R, T_old, num)
+    return R, L, inc, rc2, used
+
+
 def solve_upper_Lt(L, B):
     """solve(trimatu(L.t()), B) == L^T \\ B."""
     x, info = lapack.dtrtrs(L, B, lower=1, trans=1)
@@ -163,6 +199,17 @@ class KModel:
     SSEstar: float = 0.0
     n_jitter: int = 0
     rcond2: float = float("nan")
+    used_block_update: bool = False
+
+
+@dataclass
+class KeptModel:
+    """The committed model an update extends: m_T, m_R, m_theta and m_alpha | m_sigma2 of the reference, as
+    populate_Model's update_eligible test reads them (src/lib/Kriging.cpp:170-188)."""
+    T: np.ndarray
+    R: np.ndarray
+    theta: np.ndarray
+    extra: float | None = None
 
 
 @dataclass
@@ -182,19 +229,30 @@ class Problem:
     nugget: float = 0.0
     alpha: float = 1.0
     num: Numerics = field(default_factory=Numerics)
+    kept: KeptModel | None = None  # set by an update: the model whose factor may be block-extended
 
 
 def populate_model(pb: Problem, theta, extra=None) -> KModel:
     alpha, diag = 1.0, None
+    ex = None
     if pb.noise_model == "nugget":
-        alpha = pb.alpha if extra is None else extra
+        alpha = ex = pb.alpha if extra is None else extra
     elif pb.noise_model == "hetero":
-        s2 = pb.sigma2 if extra is None else extra
+        s2 = ex = pb.sigma2 if extra is None else extra
         diag = 1.0 + pb.noise / s2
     m = KModel()
-    m.R = build_R(pb.X, np.asarray(theta, float), pb.kernel, alpha, diag)
-    m.L, m.n_jitter, m.rcond2 = safe_chol_lower(m.R, pb.num)
+    theta = np.asarray(theta, float)
     n = pb.X.shape[0]
+    k = pb.kept
+    # update_eligible (src/lib/Kriging.cpp:170-188)
+    eligible = (k is not None and k.theta.size == theta.size and not np.any(theta - k.theta) and n > k.T.shape[0]
+                and (pb.noise_model == "none" or ex == k.extra))
+    if eligible:
+        m.R, m.L, m.n_jitter, m.rcond2, m.used_block_update = update_chol_cov(pb.X, theta, pb.kernel, alpha, diag,
+                                                                              k.T, k.R, pb.num)
+    else:
+        m.R = build_R(pb.X, theta, pb.kernel, alpha, diag)
+        m.L, m.n_jitter, m.rcond2 = safe_chol_lower(m.R, pb.num)
     # inv_sympd (LinearAlgebra.cpp:708-710)
     m.Rinv = solve_upper_Lt(m.L, solve_lower(m.L, np.eye(n)))
     m.Fstar = solve_lower(m.L, pb.F)

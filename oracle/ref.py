@@ -23,7 +23,7 @@ def available() -> bool:
 def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL", regmodel="constant",
         normalize=False, mode="eval", optim="none", theta=None, gamma=None, grad=True, reps=1,
         sigma2=None, est_sigma2=None, nugget=None, est_nugget=None, Xn=None, threads=None,
-        loovec=False, dump=False, extra_cfg=None, timeout=None):
+        loovec=False, dump=False, extra_cfg=None, timeout=None, update=None):
     """Run the reference on (X, y).  theta: (nt, d) start / evaluation point(s);
     gamma: evaluation point incl. the extra parameter (alpha | sigma2)."""
     if not available():
@@ -53,6 +53,15 @@ def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL",
             Xn = np.asfortranarray(Xn, dtype=np.float64)
             cfg["m"] = Xn.shape[0]
             Xn.T.ravel().tofile(os.path.join(wd, "Xn.bin"))
+        if update is not None:
+            # update = dict(X=..., y=..., refit=bool, noise=...): Kriging::update after the fit
+            Xu = np.asfortranarray(update["X"], dtype=np.float64)
+            cfg["update_n"] = Xu.shape[0]
+            cfg["update_refit"] = int(bool(update.get("refit", False)))
+            Xu.T.ravel().tofile(os.path.join(wd, "Xu.bin"))
+            np.ascontiguousarray(update["y"], dtype=np.float64).tofile(os.path.join(wd, "yu.bin"))
+            if update.get("noise") is not None:
+                np.ascontiguousarray(update["noise"], dtype=np.float64).tofile(os.path.join(wd, "noiseu.bin"))
         if extra_cfg:
             cfg.update(extra_cfg)
         with open(os.path.join(wd, "cfg.txt"), "w") as f:
@@ -70,6 +79,7 @@ def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL",
             raise RuntimeError(f"ref_driver failed ({out.returncode}): {out.stderr[-2000:]}")
         res = json.loads(out.stdout.strip().splitlines()[-1])
         if dump:
+            n = n + (cfg.get("update_n") or 0)
             res["T"] = np.fromfile(os.path.join(wd, "out_T.bin")).reshape(n, n, order="F")
             res["z"] = np.fromfile(os.path.join(wd, "out_z.bin"))
             M = np.fromfile(os.path.join(wd, "out_M.bin"))

@@ -8,6 +8,8 @@
 // It is used (a) to pin oracle/kriging_oracle.py, (b) to generate the fixtures
 // in tests/golden/, (c) as the CPU baseline of bench.py (kind "reference").
 //
+// With update_n=<n_u> (+ Xu.bin, yu.bin, noiseu.bin; update_refit=0|1) the fitted model is then extended by
+// Kriging::update before the outputs are written.
 // Usage: ref_driver <workdir>
 //   <workdir>/cfg.txt      key=value lines (see parse below)
 //   <workdir>/X.bin        n*d float64, column-major
@@ -145,6 +147,21 @@ int main(int argc, char** argv) {
       jvec(js, "loo_sd", std::get<1>(lv)); js << ", ";
     }
   }
+  // Kriging::update (src/lib/Kriging.cpp:2425-2660) with n_u further observations
+  const int n_u = geti("update_n", 0);
+  if (n_u > 0) {
+    arma::mat Xu(read_bin(wd + "/Xu.bin", (size_t)n_u * d).data(), n_u, d);
+    arma::vec yu(read_bin(wd + "/yu.bin", n_u).data(), n_u);
+    const bool refit = geti("update_refit", 0) != 0;
+    double t1 = now_s();
+    if (nm == Kriging::NoiseModel::Heterogeneous) {
+      arma::vec nu(read_bin(wd + "/noiseu.bin", n_u).data(), n_u);
+      k.update(yu, nu, Xu, refit);
+    } else {
+      k.update(yu, Xu, refit);
+    }
+    js << "\"update_s\": " << (now_s() - t1) << ", ";
+  }
   js.precision(17);
   jvec(js, "theta", k.theta()); js << ", ";
   jvec(js, "beta", k.beta()); js << ", ";
@@ -159,6 +176,9 @@ int main(int argc, char** argv) {
     auto pr = k.predict(Xn, true, false, false);
     jvec(js, "pred_mean", std::get<0>(pr)); js << ", ";
     jvec(js, "pred_sd", std::get<1>(pr)); js << ", ";
+  }
+  if (mode == "fit" || n_u > 0) {
+    js << "\"LL_at_model\": " << std::scientific << k.logLikelihood() << ", ";
   }
   if (dump) {
     write_bin(wd + "/out_T.bin", k.T().memptr(), k.T().n_elem);

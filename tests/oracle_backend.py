@@ -26,16 +26,41 @@ class OracleBackend:
 
     def objective(self, name, gamma, want_grad):
         self.n_objective_calls += 1
-        if name == "LL":
-            return ko.log_likelihood(self.pb, gamma, want_grad)
-        if name == "LOO":
-            return ko.leave_one_out(self.pb, gamma, want_grad)
-        return ko.log_marg_post(self.pb, gamma, want_grad)
+        try:
+            if name == "LL":
+                return ko.log_likelihood(self.pb, gamma, want_grad)
+            if name == "LOO":
+                return ko.leave_one_out(self.pb, gamma, want_grad)
+            return ko.log_marg_post(self.pb, gamma, want_grad)
+        finally:
+            self.pb.kept = None  # like the device engine: the kept factor is consumed by the first evaluation
 
     def model_scalars(self, theta, extra):
         self.theta = np.asarray(theta, float)
-        self.model = ko.populate_model(self.pb, theta, extra if self.pb.noise_model != "none" else None)
+        self.extra = extra if self.pb.noise_model != "none" else None
+        self.model = ko.populate_model(self.pb, theta, self.extra)
+        self.used_block_update = self.model.used_block_update
+        self.pb.kept = None  # like the device engine: the kept factor is consumed by the first evaluation
         return self.model.SSEstar, self.model.betahat
+
+    def commit(self):
+        self.committed = (self.model, self.theta, getattr(self, "extra", None))
+
+    def restore(self):
+        self.model, self.theta, self.extra = self.committed
+
+    def append_data(self, X_u, y_u, F_u, noise_u=None):
+        """Kriging::update, data side: the committed model (self.model at self.theta) becomes the kept factor."""
+        pb = self.pb
+        if self.model is not None:
+            pb.kept = ko.KeptModel(T=self.model.L, R=self.model.R, theta=np.asarray(self.theta, float).copy(),
+                                   extra=getattr(self, "extra", None))
+        pb.X = np.vstack([pb.X, X_u])
+        pb.y = np.concatenate([pb.y, y_u])
+        pb.F = np.vstack([pb.F, F_u])
+        if pb.noise is not None and noise_u is not None:
+            pb.noise = np.concatenate([pb.noise, noise_u])
+        self.model = None
 
     def export(self, which):
         m = self.model

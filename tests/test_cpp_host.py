@@ -62,6 +62,37 @@ def test_cpp_host_fit_default_starts(c):
         assert relerr(r["sigma2"], c["sigma2"]) < 5e-2
 
 
+with open(os.path.join(GOLDEN, "refgen_updates.json")) as _f:
+    UPD = json.load(_f)["updates"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", UPD, ids=[c["name"] for c in UPD])
+def test_cpp_host_update_matches_reference(c):
+    """lkgpu::Kriging::update against the unmodified reference's Kriging::update (tests/golden/refgen_updates.json;
+    gates as in tests/test_host_update.py)."""
+    from tests.test_host_update import update_tol
+    from tests.util import synth_update
+    X, y, noise = synth_update(c)
+    n0 = c["n0"]
+    het = c["noise_model"] == "hetero"
+    rng = np.random.Generator(np.random.PCG64(c["seed"] + 1000))
+    Xn = rng.random((25, c["d"]))
+    kw = dict(noise=noise[:n0], sigma2=c["sigma2"], est_sigma2=False) if het else {}
+    r = host.run(X[:n0], y[:n0], kernel=c["kernel"], noise_model=c["noise_model"], objective=c["objective"], mode="fit",
+                 optim=c["optim"], theta=np.full((1, c["d"]), c["theta0"]), Xn=Xn,
+                 update=dict(X=X[n0:], y=y[n0:], refit=c["refit"], noise=noise[n0:] if het else None), **kw)
+    tol = update_tol(c)
+    if not c["refit"] and not het:
+        assert r["used_block_extension"] == 1
+    assert relerr(r["theta"], c["theta"]) < tol
+    assert relerr(r["sigma2"], c["sigma2"]) < 10 * tol
+    assert relerr_vec(r["beta"], c["beta"]) < 10 * tol
+    assert relerr(r["LL_at_model"], c["LL_at_model"]) < 10 * tol
+    assert relerr_vec(r["pred_mean"], c["pred_mean"]) < tol
+    assert relerr_vec(r["pred_sd"], c["pred_sd"]) < 10 * tol
+
+
 @pytest.mark.gpu
 def test_cpp_host_objective_matches_ctypes_path():
     """Same engine behind both hosts: lkgpu::Kriging::logLikelihoodFun == _capi.Engine.objective bit for bit."""

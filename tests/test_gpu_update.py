@@ -1,0 +1,188 @@
+"""GPU parity tests of the update path, through the C ABI: lkgpu_append_data + the block
+extension of the kept factor (LinearAlgebra::update_cholCov / chol_block, src/lib/LinearAlgebra.cpp:206-299), the
+committed-model store (lkgpu_commit_model / lkgpu_restore_model) and Kriging.update against the UNMODIFIED reference's
+Kriging::update (tests/golden/refgen_updates.json)."""
+import numpy as np
+import pytest
+
+from oracle import kriging_oracle as ko
+from tests.test_host_update import UPD, check_update_case, run_update_case, update_tol
+from tests.util import relerr, relerr_vec, synth, synth_update
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from libkriging_b200 import _capi
+    _capi.lib()
+    return _capi
+
+
+# kept rows / appended rows: inside a 128-panel, on a panel boundary, below one panel, many new panels, one new row,
+# new rows that stay inside the kept factor's last panel
+LAYOUTS = [(250, 30), (256, 5), (100, 40), (200, 300), (300, 1), (130, 3), (640, 700), (1000, 24)]
+
+
+@pytest.mark.parametrize("no,nu", LAYOUTS)
+@pytest.mark.parametrize("kernel,noise_model", [("matern5_2", "none"), ("gauss", "nugget"), ("exp", "hetero")])
+def test_block_extension_equals_from_scratch(capi, no, nu, kernel, noise_model):
+    d = 4
+    X, y, noise = synth(no + nu, d, 1000 + no + nu, "smooth")
+    F = np.ones((no + nu, 1))
+    theta = np.array([0.45, 0.5, 0.55, 0.6]) * (0.5 if kernel == "gauss" else 1.0)
+    gamma = theta if noise_model == "none" else np.append(theta, 0.8 if noise_model == "nugget" else 0.7)
+    nz = noise if noise_model == "hetero" else None
+    with capi.Engine(X[:no], y[:no], F[:no], kernel=kernel, noise_model=noise_model,
+                     noise=None if nz is None else nz[:no]) as e, \
+         capi.Engine(X, y, F, kernel=kernel, noise_model=noise_model, noise=nz) as full:
+        e.objective("LL", gamma, False)
+        assert not e.last_eval_was_update
+        e.append_data(X[no:], y[no:], F[no:], None if nz is None else nz[no:])
+        assert e.n == no + nu
+        v, g, info = e.objective("LL", gamma, True, with_info=True)
+        assert e.last_eval_was_update and info["n_jitter"] == 0
+        vf, gf = full.objective("LL", gamma, True)
+        assert not full.last_eval_was_update
+        assert relerr(v, vf) < 1e-11
+        assert relerr_vec(g, gf) < 1e-9
+        L, Lf = e.export("L"), full.export("L")
+        assert np.max(np.abs(L - Lf)) < 1e-11 * np.max(np.abs(Lf))
+        assert relerr_vec(e.export("Estar"), full.export("Estar")) < 1e-10
+        # and against the oracle's restatement of the reference
+        pb = ko.Problem(X=X, y=y, F=F, kernel=kernel, noise_model=noise_model, noise=nz)
+        vo, go = ko.log_likelihood(pb, gamma, True)
+        assert relerr(v, vo) < 1e-10
+        assert relerr_vec(g, go) < 1e-9
+        # an evaluation at another point is a factorisation from scratch and drops the kept factor
+        e.objective("LL", gamma * 1.1, False)
+        assert not e.last_eval_was_update
+
+
+def test_kept_factor_is_dropped_at_another_theta(capi):
+    X, y, _ = synth(300, 3, 7, "smooth")
+    F = np.ones((300, 1))
+    th = np.full(3, 0.5)
+    with capi.Engine(X[:200], y[:200], F[:200], kernel="matern3_2") as e, \
+         capi.Engine(X, y, F, kernel="matern3_2") as full:
+        e.objective("LL", th, False)
+        e.append_data(X[200:], y[200:], F[200:])
+        v1, _ = e.objective("LL", th * 1.3, False)   # not eligible: from scratch
+        assert not e.last_eval_was_update
+        v2, _ = e.objective("LL", th, False)         # the kept factor is gone: from scratch as well
+        assert not e.last_eval_was_update
+        assert v1 == full.objective("LL", th * 1.3, False)[0]
+        assert v2 == full.objective("LL", th, False)[0]
+
+
+def test_chained_updates_and_other_objectives(capi):
+    X, y, _ = synth(500, 3, 8, "smooth")
+    F = np.ones((500, 1))
+    th = np.full(3, 0.4)
+    with capi.Engine(X[:200], y[:200], F[:200], kernel="matern5_2") as e, \
+         capi.Engine(X, y, F, kernel="matern5_2") as full:
+        e.objective("LL", th, False)
+        e.append_data(X[200:330], y[200:330], F[200:330])
+        e.objective("LL", th, False)
+        assert e.last_eval_was_update
+        e.append_data(X[330:], y[330:], F[330:])
+        loo, lg = e.objective("LOO", th, True)       # the block extension serves every objective
+        assert e.last_eval_was_update
+        loo_f, lg_f = full.objective("LOO", th, True)
+        assert relerr(loo, loo_f) < 1e-9 and relerr_vec(lg, lg_f) < 1e-8
+        lmp, mg = e.objective("LMP", th, True)
+        lmp_f, mg_f = full.objective("LMP", th, True)
+        assert lmp == lmp_f and np.array_equal(mg, mg_f)   # both from scratch now: bitwise
+
+
+def test_schur_ladder_matches_oracle(capi):
+    """Near-duplicate appended points: the ladder runs on the Schur complement only (n_jitter of the block path, kept
+    block untouched) -- a from-scratch factorisation of the same data gives a different model."""
+    c = [c for c in UPD if c["name"].startswith("upd-m52-jitter-n150+9")][0]
+    X, y, _ = synth_update(c)
+    no, n = c["n0"], c["n0"] + c["n_u"]
+    F = np.ones((n, 1))
+    th = np.full(c["d"], c["theta0"])
+    pb0 = ko.Problem(X=X[:no], y=y[:no], F=F[:no], kernel=c["kernel"])
+    m0 = ko.populate_model(pb0, th)
+    pb = ko.Problem(X=X, y=y, F=F, kernel=c["kernel"], kept=ko.KeptModel(T=m0.L, R=m0.R, theta=th))
+    m = ko.populate_model(pb, th)
+    assert m.used_block_update and m.n_jitter > 0
+    with capi.Engine(X[:no], y[:no], F[:no], kernel=c["kernel"]) as e:
+        e.objective("LL", th, False)
+        e.append_data(X[no:], y[no:], F[no:])
+        r = e.eval_raw("LL", th, want_grad=False)
+        assert e.last_eval_was_update
+        assert r["n_jitter"] == m.n_jitter
+        assert relerr(r["SSEstar"], m.SSEstar) < 1e-4   # 1e-10 added to O(1e-16) rounding residue: see test_host_update
+        L = e.export("L")
+        assert np.max(np.abs(L[:no, :no] - m0.L)) < 1e-12
+        assert np.max(np.abs(L - m.L)) < 1e-4 * np.max(np.abs(m.L))
+        r2 = e.eval_raw("LL", th, want_grad=False)       # from scratch: the ladder acts on the whole matrix
+        assert not e.last_eval_was_update
+        assert relerr(r2["SSEstar"], m.SSEstar) > 1e-2
+
+
+def test_commit_restore(capi):
+    X, y, _ = synth(400, 3, 9, "smooth")
+    F = np.ones((400, 1))
+    th = np.full(3, 0.5)
+    Xn = np.random.default_rng(1).random((30, 3))
+    with capi.Engine(X, y, F, kernel="matern5_2") as e:
+        with pytest.raises(capi.LkgpuError, match="no evaluation"):
+            e.commit_model()
+        with pytest.raises(capi.LkgpuError, match="no committed model"):
+            e.restore_model()
+        r = e.eval_raw("LL", th, want_grad=False)
+        e.commit_model()
+        m0, v0 = e.predict(Xn, np.ones((30, 1)), r["betahat"])
+        L0, z0 = e.export("L"), e.export("Estar")
+        e.objective("LOO", th * 2.0, True)
+        e.objective("LMP", th * 0.7, True)
+        e.restore_model()
+        m1, v1 = e.predict(Xn, np.ones((30, 1)), r["betahat"])
+        assert np.array_equal(m0, m1) and np.array_equal(v0, v1)
+        assert np.array_equal(L0, e.export("L")) and np.array_equal(z0, e.export("Estar"))
+        Rinv = e.export("Rinv")                       # re-derived from the restored factor
+        R = e.export("R")
+        assert np.max(np.abs(Rinv @ R - np.eye(400))) < 1e-8
+        # append extends the COMMITTED model even when another one is live
+        e.objective("LL", th * 1.5, False)
+        Xu, yu, _ = synth(50, 3, 10, "smooth")
+        e.append_data(Xu, yu, np.ones((50, 1)))
+        e.objective("LL", th, False)
+        assert e.last_eval_was_update
+
+
+@pytest.mark.parametrize("c", UPD, ids=[c["name"] for c in UPD])
+def test_update_matches_reference_on_device(c):
+    from libkriging_b200.kriging import Kriging  # noqa: F401  (default backend = the device engine)
+    k = run_update_case(c, None)
+    try:
+        if not c["refit"] and c["noise_model"] != "hetero":
+            assert k._backend.used_block_update
+        check_update_case(k, c, update_tol(c))
+    finally:
+        k.close()
+
+
+def test_update_full_size(capi):
+    """BASELINE cfg 2 size: 19000 kept + 1000 appended rows; the block extension must agree with the from-scratch
+    factorisation of all 20000 rows (1e-10) at a fraction of its cost."""
+    n, no, d = 20000, 19000, 10
+    X, y, _ = synth(n, d, 123, "smooth")
+    F = np.ones((n, 1))
+    th = np.full(d, 0.5)
+    with capi.Engine(X[:no], y[:no], F[:no], kernel="matern5_2") as e:
+        e.objective("LL", th, False)
+        e.append_data(X[no:], y[no:], F[no:])
+        v, _, info = e.objective("LL", th, False, with_info=True)
+        assert e.last_eval_was_update
+        t_upd = info["stage_ms"]["chol"]
+        g_upd = e.objective("LL", th, True)[1]
+    with capi.Engine(X, y, F, kernel="matern5_2") as full:
+        vf, gf, info_f = full.objective("LL", th, True, with_info=True)
+    assert relerr(v, vf) < 1e-10
+    assert np.array_equal(g_upd, gf)
+    print(f"block extension chol stage {t_upd:.1f} ms vs from scratch {info_f['stage_ms']['chol']:.1f} ms")
+    assert t_upd < 0.6 * info_f["stage_ms"]["chol"]

@@ -23,6 +23,19 @@ def synth(n, d, seed, yfun="prodsin"):
     return X, y, noise
 
 
+def synth_update(c):
+    """Data of an update fixture (tests/golden/make_golden_update.py): n0 + n_u rows of synth(); with c["dup"] the
+    first `dup` appended points duplicate kept ones up to 1e-8, which makes the Schur complement of the block
+    extension numerically singular (the jitter ladder then runs on it)."""
+    n0, n = c["n0"], c["n0"] + c["n_u"]
+    X, y, noise = synth(n, c["d"], c["seed"], c.get("yfun", "smooth"))
+    dup = c.get("dup", 0)
+    if dup:
+        X[n0:n0 + dup] = X[:dup] + 1e-8
+        y[n0:n0 + dup] = y[:dup] + 1e-3 * np.arange(dup)
+    return X, y, noise
+
+
 def load_reference_vectors():
     with open(os.path.join(GOLDEN, "reference_vectors.json")) as f:
         return json.load(f)
