@@ -347,9 +347,31 @@ def run_b200_arm(args):
         st = getattr(k._backend, "stats", None)
         if st:  # this rank's handle: objective calls, jitter-ladder rungs climbed, device time inside the evaluations
             fit.update(evals_this_rank=int(st["evals"]), jitter_rungs_this_rank=int(st["jitter_rungs"]),
-                       device_ms_this_rank=float(st["device_ms"]))
+                       device_ms_this_rank=float(st["device_ms"]), rungs_rejected_by_failed_factorisation=int(st["reject_info"]),
+                       rungs_rejected_by_rcond=int(st["reject_rcond"]), chol_ms_this_rank=float(st["chol_ms"]),
+                       rcond_ms_this_rank=float(st["rcond_ms"]))
         k.close()
     eng.close()
+
+    # ---- Kriging::update, no refit: the last 5 % of the rows appended to a model of the
+    #      first 95 %; block extension of the kept factor vs the from-scratch factorisation of all rows ----
+    update = None
+    if not args.no_update and rank == 0:
+        n_u = max(1, n // 20)
+        n0 = n - n_u
+        with _capi.Engine(X[:n0], y[:n0], F[:n0], kernel=KERNEL, device=local) as eu:
+            eu.objective("LL", theta, False)
+            eu.commit_model()
+            t0 = time.perf_counter()
+            eu.append_data(X[n0:], y[n0:], F[n0:])
+            t_append = time.perf_counter() - t0
+            vu, _, iu = eu.objective("LL", theta, False, with_info=True)
+            used = eu.last_eval_was_update
+            vs, _, isc = eu.objective("LL", theta, False, with_info=True)   # same point again: from scratch
+        update = {"n0": n0, "n_u": n_u, "block_extension": bool(used), "append_s": t_append,
+                  "eval_ms_block_extension": iu["stage_ms"]["total"], "chol_ms_block_extension": iu["stage_ms"]["chol"],
+                  "eval_ms_from_scratch": isc["stage_ms"]["total"], "chol_ms_from_scratch": isc["stage_ms"]["chol"],
+                  "LL_relerr_vs_from_scratch": abs(vu - vs) / abs(vs)}
 
     total_launches = int(sum_over_ranks(launches))
     if rank != 0:
@@ -421,6 +443,7 @@ def run_b200_arm(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "fit": fit,
+        "update": update,
         "stages_ms": stages,
         "result": {"LL": ll_val, "grad_norm": float(np.linalg.norm(ll_grad)), "n_jitter": last_info["n_jitter"],
                    "rcond": last_info["rcond"]},
@@ -441,6 +464,7 @@ def main():
     ap.add_argument("--d", type=int, default=10)
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-update", action="store_true")
     ap.add_argument("--smooth-y", action="store_true", help="analytic y instead of the GP draw (debug)")
     ap.add_argument("--peak", default="cublas", choices=["cublas", "max"])
     args = ap.parse_args()

@@ -56,7 +56,10 @@ enum {
   LKGPU_ST_LAUUM = 5,   /* "R^-1 = L^-T * L^-1"                 */
   LKGPU_ST_GRAD = 6,    /* "gradR computation"                  */
   LKGPU_ST_EXTRA = 7,   /* LOO / LMP specific work              */
-  LKGPU_ST_TOTAL = 8    /* whole evaluation, device time        */
+  LKGPU_ST_TOTAL = 8,   /* whole evaluation, device time        */
+  /* counters kept in the spare slots (not times): rungs of safe_chol_lower's ladder rejected ...            */
+  LKGPU_CT_REJECT_INFO = 9,   /* ... because the factorisation failed (non-positive pivot; attempt aborted) */
+  LKGPU_CT_REJECT_RCOND = 10  /* ... because rcond_1(L)^2 < min_rcond                                      */
 };
 
 typedef struct lkgpu_out {
@@ -176,6 +179,13 @@ void* lkgpu_get_stream(void* handle);
 /* FP64 DMMA peak probe (dependent-free mma.sync.m8n8k4.f64 chains on every SM):
  * returns TFLOP/s in *tflops.  Used by bench.py for the roofline denominator. */
 int lkgpu_probe_fp64_peak(int device, int mode, double* tflops);
+
+/* Tell a handle that it is one of several that evaluate at the same time on its device (one per multistart row in
+ * flight, BASELINE cfg 5; one per NestedKriging sub-model).  Such a handle always takes the launch-chain triangular
+ * sweeps and host-separated TRTRI launches, so its results do not depend on what else happens to be running (they are
+ * reproducible bit for bit).  An unflagged handle decides per evaluation: the persistent wavefront sweeps when it has
+ * the device to itself -- other handles' evaluations then wait for it -- the launch chain otherwise. */
+int lkgpu_set_concurrent(void* handle, int flag);
 
 /* Free / total bytes of device memory: the host sizes the number of concurrent handles (one per
  * multistart row in flight, BASELINE cfg 5) with it.  The reference preallocates one KModel per start

@@ -21,6 +21,7 @@ EXPORTS = {"L": 0, "R": 1, "Rinv": 2, "Fstar": 3, "Rstar": 4, "ystar": 5, "Estar
            "loo_err": 9, "loo_s2": 10}
 N_STAGES = 12
 STAGE_NAMES = ["cov", "chol", "rcond", "solves", "trtri", "lauum", "grad", "extra", "total"]
+COUNTER_NAMES = {"reject_info": 9, "reject_rcond": 10}  # spare stage_ms slots used as counters (include/lkgpu.h)
 
 _dp = C.POINTER(C.c_double)
 
@@ -64,6 +65,7 @@ def lib():
     L.lkgpu_predict.argtypes = [vp, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp]
     L.lkgpu_set_data.argtypes = [vp, _dp, _dp, _dp, _dp]
     L.lkgpu_append_data.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp]
+    L.lkgpu_set_concurrent.argtypes = [vp, C.c_int]
     L.lkgpu_commit_model.argtypes = [vp]
     L.lkgpu_restore_model.argtypes = [vp]
     L.lkgpu_last_eval_was_update.argtypes = [vp]
@@ -160,6 +162,10 @@ class Engine:
         _check(lib().lkgpu_append_data(self._h, n_u, _ptr(X_u), _ptr(y_u), _ptr(F_u), _ptr(nz)))
         self.n += n_u
 
+    def set_concurrent(self, flag=True):
+        """This handle is one of several evaluating at the same time on its device (lkgpu_set_concurrent)."""
+        _check(lib().lkgpu_set_concurrent(self._h, int(bool(flag))))
+
     def commit_model(self):
         """Snapshot the model of the last evaluation as the committed model (m_T, m_M, m_z, ... of the reference)."""
         _check(lib().lkgpu_commit_model(self._h))
@@ -208,7 +214,8 @@ class Engine:
                                          C.byref(val), _ptr(grad), C.byref(out)))
         if with_info:
             info = dict(n_jitter=out.n_jitter, rcond=out.rcond, SSEstar=out.SSEstar, sum_log_diagL=out.sum_log_diagL,
-                        S2=out.S2, stage_ms={k: out.stage_ms[i] for i, k in enumerate(STAGE_NAMES)})
+                        S2=out.S2, stage_ms={k: out.stage_ms[i] for i, k in enumerate(STAGE_NAMES)},
+                        **{k: int(out.stage_ms[i]) for k, i in COUNTER_NAMES.items()})
             return val.value, grad, info
         return val.value, grad
 

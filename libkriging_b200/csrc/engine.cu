@@ -9,8 +9,10 @@
 //   Bv N x (p+1) : [F | y] -> [Fstar | ystar] ;  Ev, Xv : N vectors (Estar, x)
 // No CPU fallback anywhere: every entry point needs a CUDA device.
 #include <algorithm>
-#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,8 +33,17 @@ using namespace lk;
 namespace {
 
 thread_local std::string g_last_error;
-// live handles per device: the sweeps choose their kernel by it (see Engine::solve_fwd)
-std::atomic<int> g_live_handles[64];
+// Per-device gate deciding which sweep kernel an evaluation uses (see Engine::SweepGate): the persistent wavefront
+// kernel only when no other handle evaluates on the device at the same time.
+struct DeviceGate {
+  std::mutex m;
+  std::condition_variable cv;
+  int active = 0;       // evaluations in flight on this device
+  int wave_active = 0;  // ... of which chose the wavefront kernel (0 or 1)
+  int waiting = 0;      // threads blocked at the gate behind a wavefront-mode evaluation
+  std::chrono::steady_clock::time_point last_multi{};  // last time two evaluations overlapped (or queued)
+};
+DeviceGate g_gate[64];
 
 struct LkError {
   std::string msg;
@@ -270,11 +281,7 @@ struct Engine {
   } cm;
   bool live_is_committed = false;
 
-  bool registered = false;
-  ~Engine() {
-    release();
-    if (registered) g_live_handles[device & 63].fetch_sub(1);
-  }
+  ~Engine() { release(); }
   // everything whose size depends on n (lkgpu_append_data re-creates these for the extended data set)
   void release_sized() {
     cudaSetDevice(device);
@@ -382,8 +389,6 @@ struct Engine {
     alloc_sized(noise != nullptr);
     set_data(X, y, F, noise);
     CUDA_CHECK(cudaStreamSynchronize(s_main));
-    g_live_handles[device & 63].fetch_add(1);
-    registered = true;
   }
 
   // device workspaces, tensor maps and tile plans for the current n (a1: KModel)
@@ -890,7 +895,14 @@ struct Engine {
       a.epilogue = EPI_SETNEG;
       a.table = trtri_tables + lv.off2;
       a.ntiles = (int)lv.n2;
+      // Overlapping evaluations: the host waits for each level's first product before launching the second.
+      // TRTRI is the one place where a kernel consumes, through TMA and within microseconds, what the previous
+      // kernel stored; with several handles in flight a stale 32-byte sector was still read there about once in
+      // 2000 evaluations even with the writer-side fences (never with host-separated launches, never with one
+      // handle).  16 waits of ~10 us per evaluation.
+      if (chain_mode) CUDA_CHECK(cudaStreamSynchronize(s_main));
       gemm(1, mapW, W, mapV, V, a, s_main, true);
+      if (chain_mode) CUDA_CHECK(cudaStreamSynchronize(s_main));
     }
     have_W = true;
   }
@@ -933,15 +945,49 @@ struct Engine {
     }
   }
   // ---- triangular sweeps (a5): one persistent wavefront kernel per sweep (trsv_wave.cuh) ----
-  // With ONE handle on the device the persistent wavefront kernel runs (3 sweeps in 2.3 ms at n = 20000).  With
-  // several handles evaluating concurrently (multistart rows in flight, BASELINE cfg 5) it does not: measured on
-  // B200, ~1.5 % of its sweeps then return a wrong block -- even with a single CTA, i.e. without any inter-CTA
-  // traffic, and with every producer of its TMA operands fenced -- while the launch-chain kernels below, which read
-  // L through ordinary loads, never did (0 of 1080 evaluations).  Until that is understood, concurrent handles
-  // take the launch chain (n <= 8192 there: 40-64 short launches per sweep).  LKGPU_WAVE_ALWAYS=1 overrides.
-  bool sweeps_by_launch_chain() const {
-    return use_step_trsv || (!wave_always && g_live_handles[device & 63].load() > 1);
-  }
+  // With ONE evaluation in flight on the device the persistent wavefront kernel runs (3 sweeps in 2.3 ms at
+  // n = 20000).  With several handles evaluating concurrently (multistart rows in flight, BASELINE cfg 5) it does
+  // not: measured on B200, ~1.5 % of its sweeps then return a wrong block -- even with a single CTA, i.e. without any
+  // inter-CTA traffic, and with every producer of its TMA operands fenced -- while the launch-chain kernels below,
+  // which read L through ordinary loads, never did (0 of 1900 evaluations).  Until that is understood, overlapping
+  // evaluations take the launch chain (n <= 8192 there: 40-64 short launches per sweep).  The gate makes the choice
+  // race-free: an evaluation that found the device to itself runs in wavefront mode and later arrivals wait for it
+  // (once), after which they all proceed together in launch-chain mode; a device that saw overlapping evaluations
+  // in the last two seconds stays in launch-chain mode.  LKGPU_WAVE_ALWAYS=1 / LKGPU_STEP_TRSV=1 override.
+  bool chain_mode = false;
+  bool concurrent_flag = false;  // lkgpu_set_concurrent: this handle is one of several evaluating at the same time
+  struct SweepGate {
+    Engine& e;
+    bool wave = false;
+    explicit SweepGate(Engine& e_) : e(e_) {
+      DeviceGate& g = g_gate[e.device & 63];
+      std::unique_lock<std::mutex> lk(g.m);
+      const auto now = std::chrono::steady_clock::now();
+      if (g.wave_active > 0) {
+        ++g.waiting;
+        g.last_multi = now;
+        g.cv.wait(lk, [&] { return g.wave_active == 0; });
+        --g.waiting;
+      }
+      ++g.active;
+      const bool recent_multi = g.last_multi.time_since_epoch().count() != 0 &&
+                                std::chrono::steady_clock::now() - g.last_multi < std::chrono::seconds(2);
+      if (g.active > 1 || g.waiting > 0) g.last_multi = std::chrono::steady_clock::now();
+      wave = e.wave_always || (!e.concurrent_flag && g.active == 1 && g.waiting == 0 && !recent_multi);
+      if (wave && !e.wave_always) g.wave_active = 1;
+      e.chain_mode = !wave;
+    }
+    ~SweepGate() {
+      DeviceGate& g = g_gate[e.device & 63];
+      {
+        std::lock_guard<std::mutex> lk(g.m);
+        --g.active;
+        if (wave && !e.wave_always) g.wave_active = 0;
+      }
+      g.cv.notify_all();
+    }
+  };
+  bool sweeps_by_launch_chain() const { return use_step_trsv || chain_mode; }
   void solve_fwd(double* B, int nrhs) {
     if (sweeps_by_launch_chain()) return solve_fwd_steps(B, nrhs);
     solve_wave<false>(B, nrhs);
@@ -1144,6 +1190,7 @@ struct Engine {
   // =====================  one objective evaluation  =====================
   void eval(int objective, const double* theta, double extra, int want_grad, lkgpu_out* out) {
     CUDA_CHECK(cudaSetDevice(device));
+    SweepGate gate(*this);
     if (objective != LKGPU_OBJ_LL && objective != LKGPU_OBJ_LOO && objective != LKGPU_OBJ_LMP)
       throw LkError{"lkgpu_eval: unknown objective"};
     if (objective == LKGPU_OBJ_LOO && noise_model != LKGPU_NOISE_NONE)
@@ -1170,6 +1217,7 @@ struct Engine {
     int inc = 0;
     double rc2 = 0.0;
     float ms_cov = 0, ms_chol = 0, ms_rcond = 0, ms_trtri = 0;
+    int n_attempt_info = 0, n_attempt_rcond = 0;  // rejected rungs: failed factorisation / rcond below min_rcond
     // ---- populate_Model's update_eligible (Kriging.cpp:170-188): same theta / extra as the kept factor and more
     //      rows than it has -> block extension; anything else (or an exhausted ladder there) -> from scratch ----
     bool updated = false;
@@ -1236,6 +1284,7 @@ struct Engine {
         rc2 = NAN;
       }
       if (!ok || wrong_rcond) {
+        if (!ok) ++n_attempt_info; else ++n_attempt_rcond;
         if (inc > max_inc)
           throw LkError{"[ERROR] Exceed max numerical nugget (" + std::to_string(inc) + " x 1e" +
                         std::to_string(std::log10(num_nugget)) + ") added to force chol matrix"};
@@ -1265,6 +1314,8 @@ struct Engine {
     out->stage_ms[LKGPU_ST_CHOL] = ms_chol;
     out->stage_ms[LKGPU_ST_RCOND] = ms_rcond;
     out->stage_ms[LKGPU_ST_TRTRI] = ms_trtri;
+    out->stage_ms[LKGPU_CT_REJECT_INFO] = n_attempt_info;
+    out->stage_ms[LKGPU_CT_REJECT_RCOND] = n_attempt_rcond;
 
     // ---- sum log diag L ----
     launches += 1;
@@ -1619,6 +1670,13 @@ int lkgpu_restore_model(void* handle) {
   LK_TRY
   if (!handle) throw LkError{"null handle"};
   static_cast<Engine*>(handle)->restore();
+  LK_CATCH
+}
+
+int lkgpu_set_concurrent(void* handle, int flag) {
+  LK_TRY
+  if (!handle) throw LkError{"null handle"};
+  static_cast<Engine*>(handle)->concurrent_flag = flag != 0;
   LK_CATCH
 }
 

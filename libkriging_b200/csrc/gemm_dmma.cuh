@@ -171,22 +171,21 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (args.abort_flag != nullptr) {
-    // one read per CTA, so that the whole CTA takes the same branch even if the flag is raised right now
-    __shared__ int s_abort;
-    if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(args.abort_flag);
-    __syncthreads();
-    if (s_abort != 0) return;
-  }
-
+  // Abort flag: one read per CTA (so that the whole CTA takes the same branch even if the flag is raised right
+  // now), issued before the barrier initialisation so that its latency hides behind it.
+  __shared__ int s_abort;
   if (threadIdx.x == 0) {
+    int aborted = 0;
+    if (args.abort_flag != nullptr) aborted = *reinterpret_cast<const volatile int*>(args.abort_flag);
     for (int s = 0; s < GSTAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], GEMM_CONSUMER_WARPS);
     }
     fence_barrier_init();
+    s_abort = aborted;
   }
   __syncthreads();
+  if (s_abort != 0) return;
 
   // ===================== TMA producer: thread 0, inline in consumer warp 0 =====================
   // Four warps per CTA and two CTAs per SM = two warps per SM sub-partition, so each thread may hold the

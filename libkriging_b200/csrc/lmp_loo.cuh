@@ -371,6 +371,7 @@ void Engine::predict(int m, const double* Xn, const double* Fn, const double* be
   CUDA_CHECK(cudaSetDevice(device));
   if (!have_model) throw LkError{"lkgpu_predict: no evaluation has been run on this handle"};
   if (m < 1) throw LkError{"lkgpu_predict: need m >= 1"};
+  SweepGate gate(*this);
   for (int k = 0; k < d; ++k) kp.inv_theta[k] = 1.0 / last_theta[k];
   std::vector<double> hRstar((size_t)p * p);
   CUDA_CHECK(cudaMemcpy(hRstar.data(), dRstar, (size_t)p * p * 8, cudaMemcpyDeviceToHost));

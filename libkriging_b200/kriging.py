@@ -39,7 +39,7 @@ class GpuBackend:
         self._scalars_key = None
         self._scalars = None
         # running totals over this handle's objective calls (bench.py reports them for the fit)
-        self.stats = dict(evals=0, jitter_rungs=0, device_ms=0.0)
+        self.stats = dict(evals=0, jitter_rungs=0, device_ms=0.0, reject_info=0, reject_rcond=0, chol_ms=0.0, rcond_ms=0.0)
 
     def set_params(self, est_sigma2, sigma2, est_nugget, nugget, alpha):
         self.engine.set_params(est_sigma2, sigma2, est_nugget, nugget, alpha)
@@ -58,6 +58,10 @@ class GpuBackend:
         st["evals"] += 1
         st["jitter_rungs"] += int(info["n_jitter"])
         st["device_ms"] += float(info["stage_ms"]["total"])
+        st["reject_info"] += int(info.get("reject_info", 0))
+        st["reject_rcond"] += int(info.get("reject_rcond", 0))
+        st["chol_ms"] += float(info["stage_ms"]["chol"])
+        st["rcond_ms"] += float(info["stage_ms"]["rcond"])
         return val, grad
 
     def model_scalars(self, theta, extra):
@@ -76,6 +80,9 @@ class GpuBackend:
         theta (lkgpu_append_data)."""
         self.engine.append_data(X_u, y_u, F_u, noise_u)
         self._scalars_key = None
+
+    def set_concurrent(self, flag=True):
+        self.engine.set_concurrent(flag)
 
     def commit(self):
         """The model of the last evaluation becomes the committed one (Kriging.cpp:2156-2173)."""
@@ -173,7 +180,7 @@ class Kriging:
     NoiseKriging == noise_model="hetero" (reference Kriging.hpp:45-49)."""
 
     def __init__(self, kernel: str, noise_model: str = "none", *, device: int | None = None, backend_factory=None,
-                 concurrent_starts: int | None = None):
+                 concurrent_starts: int | None = None, concurrent_handle: bool = False):
         if kernel not in ("gauss", "exp", "matern3_2", "matern5_2"):
             raise ValueError(f"Unsupported covariance kernel: {kernel}")
         nm = _NOISE_ALIASES.get(noise_model.lower())
@@ -185,6 +192,8 @@ class Kriging:
         self._backend_factory = backend_factory or _default_backend_factory
         self._backend = None
         self._concurrent_starts = concurrent_starts
+        # True: this model is one of several being fitted at the same time on the device (nested.fit_submodels)
+        self._concurrent_handle = bool(concurrent_handle)
         self.config = _optim.OptimConfig.from_env()
         self.m_is_empty = True
         self.fit_log = {}
@@ -278,6 +287,8 @@ class Kriging:
         dev = self._device if self._device is not None else (comm.device if comm is not None else 0)
         be = self._backend = self._backend_factory(self.m_X, self.m_y, self.m_F, self.m_kernel, self.m_noise_model,
                                                    self.m_noise, dev)
+        if self._concurrent_handle and hasattr(be, "set_concurrent"):
+            be.set_concurrent(True)
         self.m_sigma2, self.m_nugget, self.m_alpha = 1.0, 0.0, 1.0
         self.m_is_empty = True
         sigma2_p = parameters.get("sigma2")
@@ -455,16 +466,22 @@ class Kriging:
             # streams"): a mid-size factorisation cannot fill 148 SMs (its panel chain is latency-bound), so this
             # rank's starts run concurrently, one engine handle (own workspaces, own streams) and one host thread
             # each.  Evaluations are deterministic (fixed-order reductions), so every start's trajectory is
-            # bitwise the one the sequential loop produces; the argmin below is still taken in start order.
+            # reproducible bit for bit and equals the sequential loop's up to the rounding of the triangular sweeps
+            # (overlapping evaluations use the launch-chain sweep kernels: engine.cu, SweepGate); the argmin below
+            # is still taken in start order.
             import queue
             from concurrent.futures import ThreadPoolExecutor
             pool_be = queue.SimpleQueue()
             pool_be.put(be)
+            if hasattr(be, "set_concurrent"):
+                be.set_concurrent(True)
             extra_be = []
             for _ in range(ncon - 1):
                 b = self._backend_factory(self.m_X, self.m_y, self.m_F, self.m_kernel, self.m_noise_model,
                                           self.m_noise, dev)
                 b.set_params(self.m_est_sigma2, self.m_sigma2, self.m_est_nugget, self.m_nugget, self.m_alpha)
+                if hasattr(b, "set_concurrent"):
+                    b.set_concurrent(True)
                 extra_be.append(b)
                 pool_be.put(b)
 
@@ -481,6 +498,8 @@ class Kriging:
             finally:
                 for b in extra_be:
                     b.close()
+                if hasattr(be, "set_concurrent") and not self._concurrent_handle:
+                    be.set_concurrent(False)
 
         # ---- argmin over successful starts, strict '<' in start order (Kriging.cpp:2097-2114) ----
         if comm is None:

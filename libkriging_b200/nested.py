@@ -7,7 +7,8 @@ every sub-model in closed form (unify_hyperparameters, :277-331).  A sub-model i
 (n / p rows) whose panel chain is latency-bound and cannot fill 148 SMs: here the p fits run concurrently, one engine
 handle (own workspaces, own CUDA streams) and one host thread per fit in flight -- the same batched-occupancy
 mechanism as the concurrent multistart rows of Kriging.fit (BASELINE cfg 5).  Evaluations are deterministic, so every
-sub-model is bitwise the one a sequential loop produces.  Across GPUs the groups shard like multistart rows
+sub-model is reproducible bit for bit and is the one a sequential loop produces up to the rounding of the triangular
+sweeps (overlapping evaluations use the launch-chain sweep kernels: engine.cu, SweepGate).  Across GPUs the groups shard like multistart rows
 (group g on rank g mod world); only the fitted hyper-parameters (d + 2 doubles per group) are exchanged.
 
 Out of scope (reference control plane): the k-means partition (arma::kmeans with arma's own RNG), the PoE / BCM /
@@ -59,7 +60,8 @@ def fit_submodels(y, X, groups, kernel, regmodel="constant", optim="BFGS", objec
 
     def fit_one(g):
         idx = np.asarray(groups[g], dtype=np.int64)
-        k = Kriging(kernel, device=dev, backend_factory=backend_factory, concurrent_starts=1)
+        k = Kriging(kernel, device=dev, backend_factory=backend_factory, concurrent_starts=1,
+                    concurrent_handle=concurrent > 1)
         k.fit(y[idx], X[idx], regmodel, False, optim, objective, parameters)
         return g, k
 

@@ -41,6 +41,18 @@ class MultistartComm:
     def my_starts(self, multistart: int):
         return [s for s in range(multistart) if s % self.world == self.rank]
 
+    def allreduce_sum(self, arr):
+        """Element-wise sum over ranks of a float64 array (NestedKriging sub-model hyper-parameters: d + 2 doubles per
+        group, each group owned by exactly one rank)."""
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.tdev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy().copy()
+
+    def allreduce_max(self, value):
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.tdev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
     def argmin_exchange(self, results: dict, multistart: int, gd: int):
         """results: {start_index: dict(success, objective_value, gamma, n_eval)} for this rank's starts.
         Returns (best_idx, min_objective, gamma*, total number of evaluations over all ranks)."""

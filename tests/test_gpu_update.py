@@ -44,11 +44,11 @@ def test_block_extension_equals_from_scratch(capi, no, nu, kernel, noise_model):
         assert e.last_eval_was_update and info["n_jitter"] == 0
         vf, gf = full.objective("LL", gamma, True)
         assert not full.last_eval_was_update
-        assert relerr(v, vf) < 1e-11
+        assert relerr(v, vf) < 1e-10   # north_star's objective tolerance (two factorisation orders of the same matrix)
         assert relerr_vec(g, gf) < 1e-9
         L, Lf = e.export("L"), full.export("L")
         assert np.max(np.abs(L - Lf)) < 1e-11 * np.max(np.abs(Lf))
-        assert relerr_vec(e.export("Estar"), full.export("Estar")) < 1e-10
+        assert relerr_vec(e.export("Estar"), full.export("Estar")) < 1e-9
         # and against the oracle's restatement of the reference
         pb = ko.Problem(X=X, y=y, F=F, kernel=kernel, noise_model=noise_model, noise=nz)
         vo, go = ko.log_likelihood(pb, gamma, True)
