@@ -347,6 +347,7 @@ void Engine::loo_finish(int want_grad) {
       std::vector<TileDesc> lt;
       for (int rt = 0; rt < 2 * nb; ++rt)
         for (int ct = 0; 2 * ct <= rt; ++ct) lt.push_back({rt * TM, ct * TN, 0, N});
+      if (l2_order) order_for_l2(lt);
       loo_tiles = (int)lt.size();
       loo_table = dalloc<TileDesc>(lt.size());
       CUDA_CHECK(cudaMemcpy(loo_table, lt.data(), lt.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));

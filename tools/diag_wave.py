@@ -16,7 +16,7 @@ X, y, _ = synth(n, d, 505, "smooth")
 F = np.ones((n, 1))
 th = np.full(d, 1.0)
 with _capi.Engine(X, y, F, kernel="gauss") as e:
-    e.objective("LL", th, False)   # value only: no TRTRI in the way
+    e.objective("LL", th, True)
     ref = {k: e.export(k) for k in ("x", "Estar", "ystar", "Fstar")}
 engines = [_capi.Engine(X, y, F, kernel="gauss") for _ in range(nthreads)]
 lock = threading.Lock()
@@ -26,7 +26,7 @@ cnt = [0]
 def worker(t):
     e = engines[t]
     for r in range(reps):
-        e.objective("LL", th, False)
+        e.objective("LL", th, True)
         for k, fwd in (("ystar", True), ("Fstar", True), ("Estar", True), ("x", False)):
             v = e.export(k).ravel()
             bad = np.flatnonzero(v != ref[k].ravel())
@@ -40,7 +40,8 @@ def worker(t):
                           % (t, r, k, "fwd" if fwd else "bwd", bad.size, blk, inblk.size, inblk[0], inblk[-1],
                              abs(v[org] - ref[k].ravel()[org]), ref[k].ravel()[org]), flush=True)
                     print("      in-block pattern (16-row groups):", "".join(
-                        "X" if ((inblk >= g) & (inblk < g + 16)).any() else "." for g in range(0, 128, 16)), flush=True)
+                        "X" if ((inblk >= g) & (inblk < g + 16)).any() else "." for g in range(0, 128, 16)),
+                        " rel.diff per 16-row group: " + " ".join("%.0e" % (np.max(np.abs(v[blk * 128 + g:blk * 128 + g + 16] - ref[k].ravel()[blk * 128 + g:blk * 128 + g + 16])) / (np.max(np.abs(ref[k].ravel()[blk * 128:blk * 128 + 128])) + 1e-300)) for g in range(0, min(128, v.size - blk * 128), 16)), flush=True)
 
 
 ths = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
