@@ -180,11 +180,12 @@ void* lkgpu_get_stream(void* handle);
  * returns TFLOP/s in *tflops.  Used by bench.py for the roofline denominator. */
 int lkgpu_probe_fp64_peak(int device, int mode, double* tflops);
 
-/* Tell a handle that it is one of several that evaluate at the same time on its device (one per multistart row in
- * flight, BASELINE cfg 5; one per NestedKriging sub-model).  Such a handle always takes the launch-chain triangular
- * sweeps and host-separated TRTRI launches, so its results do not depend on what else happens to be running (they are
- * reproducible bit for bit).  An unflagged handle decides per evaluation: the persistent wavefront sweeps when it has
- * the device to itself -- other handles' evaluations then wait for it -- the launch chain otherwise. */
+/* Evaluations of different handles on one device are exclusive by default: they queue, and only their host work
+ * overlaps.  Handles flagged here overlap with each other (one per multistart row in flight, BASELINE cfg 5; one per
+ * NestedKriging sub-model): the throughput mode for many mid-size factorisations.  Known issue, measured on B200 and
+ * documented in DESIGN.md ("Concurrent handles"): with the grids of several handles resident together an evaluation
+ * has a 0.03 % (4 handles) .. 0.5 % (8 handles) chance of a tile computed from stale operand data (relative error
+ * 1e-6 .. 1e-2 in the gradient); a lone or exclusive evaluation has never shown it. */
 int lkgpu_set_concurrent(void* handle, int flag);
 
 /* Free / total bytes of device memory: the host sizes the number of concurrent handles (one per

@@ -33,15 +33,14 @@ using namespace lk;
 namespace {
 
 thread_local std::string g_last_error;
-// Per-device gate deciding which sweep kernel an evaluation uses (see Engine::SweepGate): the persistent wavefront
-// kernel only when no other handle evaluates on the device at the same time.
+// Per-device gate (see Engine::SweepGate): by default the evaluations of different handles never overlap on a
+// device; handles flagged by lkgpu_set_concurrent overlap with each other.
 struct DeviceGate {
   std::mutex m;
   std::condition_variable cv;
-  int active = 0;       // evaluations in flight on this device
-  int wave_active = 0;  // ... of which chose the wavefront kernel (0 or 1)
-  int waiting = 0;      // threads blocked at the gate behind a wavefront-mode evaluation
-  std::chrono::steady_clock::time_point last_multi{};  // last time two evaluations overlapped (or queued)
+  int shared_active = 0;       // evaluations of flagged handles in flight
+  bool exclusive_active = false;
+  int exclusive_waiting = 0;   // unflagged evaluations waiting for the device (flagged newcomers queue behind them)
 };
 DeviceGate g_gate[64];
 
@@ -90,11 +89,17 @@ CUtensorMap make_map(double* base, long long rows, long long cols, long long ld,
   return m;
 }
 
+// The tensor maps of one matrix live in DEVICE memory, one allocation per matrix that is written once and never
+// modified; kernels receive pointers to them.  (They used to be passed by value as __grid_constant__ kernel
+// parameters.  With 8 handles launching the same kernels concurrently, TMA loads then occasionally fetched a tile
+// of ANOTHER handle's matrix -- same coordinates, other buffer: relative errors of 1e-6..1e-3 in single tiles, about
+// one evaluation in 300 -- consistent with a descriptor cached by parameter-space address outliving its launch.
+// A descriptor at an address of its own cannot alias.)
 struct MatMaps {
-  CUtensorMap mm;  // M-major operand tiles: box {16 rows, 16 k-columns}
-  CUtensorMap km;  // K-major operand tiles: box {16 k-rows, 64 columns}
-  CUtensorMap wf;  // wavefront sweep, forward: box {128 rows, 32 columns}, dense
-  CUtensorMap wb;  // wavefront sweep, backward: box {16 rows, 128 columns}, SWIZZLE_128B
+  const CUtensorMap* mm = nullptr;  // M-major operand tiles: box {16 rows, 16 k-columns}
+  const CUtensorMap* km = nullptr;  // K-major operand tiles: box {16 k-rows, 64 columns}
+  const CUtensorMap* wf = nullptr;  // wavefront sweep, forward: box {128 rows, 32 columns}, dense
+  const CUtensorMap* wb = nullptr;  // wavefront sweep, backward: box {16 rows, 128 columns}, SWIZZLE_128B
 };
 
 // FP64 peak probe kernels ---------------------------------------------------
@@ -297,6 +302,8 @@ struct Engine {
     if (lauum_table) cudaFree(lauum_table);
     if (loo_table) cudaFree(loo_table);
     if (hpin) cudaFreeHost(hpin);
+    for (CUtensorMap* m : map_allocs) cudaFree(m);
+    map_allocs.clear();
     for (auto e : ev_panel) cudaEventDestroy(e);
     for (auto e : ev_upd) cudaEventDestroy(e);
     {
@@ -393,6 +400,25 @@ struct Engine {
     CUDA_CHECK(cudaStreamSynchronize(s_main));
   }
 
+  std::vector<CUtensorMap*> map_allocs;  // device copies of the tensor maps (freed with the sized buffers)
+  MatMaps maps_of(double* buf, bool with_sweep_maps) {
+    CUtensorMap h[4];
+    h[0] = make_map(buf, N, N, ld, 16, 16);
+    h[1] = make_map(buf, N, N, ld, 16, 64);
+    if (with_sweep_maps) {
+      h[2] = make_map(buf, N, N, ld, 128, 32, false);
+      h[3] = make_map(buf, N, N, ld, 16, 128);
+    } else {
+      h[2] = h[0];
+      h[3] = h[0];
+    }
+    CUtensorMap* dm = nullptr;
+    CUDA_CHECK(cudaMalloc(&dm, 4 * sizeof(CUtensorMap)));
+    map_allocs.push_back(dm);
+    CUDA_CHECK(cudaMemcpy(dm, h, 4 * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    return MatMaps{dm + 0, dm + 1, dm + 2, dm + 3};
+  }
+
   // device workspaces, tensor maps and tile plans for the current n (a1: KModel)
   void alloc_sized(bool with_noise) {
     N = ((n + BLK - 1) / BLK) * BLK;
@@ -439,13 +465,9 @@ struct Engine {
     CUDA_CHECK(cudaMemsetAsync(W, 0, (size_t)N * N * 8, s_main));
     CUDA_CHECK(cudaMemsetAsync(V, 0, (size_t)N * N * 8, s_main));
     CUDA_CHECK(cudaMemsetAsync(A, 0, (size_t)N * N * 8, s_main));
-    auto maps_of = [&](double* buf) {
-      return MatMaps{make_map(buf, N, N, ld, 16, 16), make_map(buf, N, N, ld, 16, 64),
-                     make_map(buf, N, N, ld, 128, 32, false), make_map(buf, N, N, ld, 16, 128)};
-    };
-    mapA = maps_of(A);
-    mapW = maps_of(W);
-    mapV = maps_of(V);
+    mapA = maps_of(A, true);
+    mapW = maps_of(W, true);
+    mapV = maps_of(V, true);
     wave_ctl = dalloc<int>(nb + 1);
     build_plans();
   }
@@ -459,6 +481,7 @@ struct Engine {
   }
   void commit() {
     CUDA_CHECK(cudaSetDevice(device));
+    SweepGate gate(*this);
     if (!have_model) throw LkError{"lkgpu_commit_model: no evaluation has been run on this handle"};
     if (!cm.L) {
       cm.L = dalloc<double>((size_t)N * N);
@@ -491,6 +514,7 @@ struct Engine {
   }
   void restore() {
     CUDA_CHECK(cudaSetDevice(device));
+    SweepGate gate(*this);
     if (!cm.valid) throw LkError{"lkgpu_restore_model: no committed model on this handle"};
     if (live_is_committed) return;
     dev_copy(A, cm.L, (long long)N * N);
@@ -522,6 +546,7 @@ struct Engine {
   // a factorisation from scratch: populate_Model's `update_eligible` (Kriging.cpp:170-188).
   void append(int n_u, const double* X_u, const double* y_u, const double* F_u, const double* noise_u) {
     CUDA_CHECK(cudaSetDevice(device));
+    SweepGate gate(*this);
     if (n_u < 1) throw LkError{"lkgpu_append_data: need n_u >= 1"};
     if (noise_model == LKGPU_NOISE_HETERO && !noise_u) throw LkError{"lkgpu_append_data: heterogeneous noise needs noise_u"};
     if (cm.valid && !live_is_committed) restore();  // the factor that is extended is the committed one (m_T)
@@ -970,8 +995,8 @@ struct Engine {
       double* Bq = B + (long long)q0 * N;
       dev_zero_ints(wave_ctl, nb + 1);
       ++launches;
-      const CUtensorMap& mL = BWD ? mapA.wb : mapA.wf;
-      const CUtensorMap& mW = BWD ? mapW.wb : mapW.wf;
+      const CUtensorMap* mL = BWD ? mapA.wb : mapA.wf;
+      const CUtensorMap* mW = BWD ? mapW.wb : mapW.wf;
       if (nq == 1)
         trsv_wave_kernel<BWD, 1><<<grid, WAVE_THREADS, wave_smem_bytes(1), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl);
       else if (nq == 2)
@@ -984,44 +1009,48 @@ struct Engine {
     }
   }
   // ---- triangular sweeps (a5): one persistent wavefront kernel per sweep (trsv_wave.cuh) ----
-  // With ONE evaluation in flight on the device the persistent wavefront kernel runs (3 sweeps in 2.3 ms at
-  // n = 20000).  With several handles evaluating concurrently (multistart rows in flight, BASELINE cfg 5) it does
-  // not: measured on B200, ~1.5 % of its sweeps then return a wrong block -- even with a single CTA, i.e. without any
-  // inter-CTA traffic, and with every producer of its TMA operands fenced -- while the launch-chain kernels below,
-  // which read L through ordinary loads, never did (0 of 1900 evaluations).  Until that is understood, overlapping
-  // evaluations take the launch chain (n <= 8192 there: 40-64 short launches per sweep).  The gate makes the choice
-  // race-free: an evaluation that found the device to itself runs in wavefront mode and later arrivals wait for it
-  // (once), after which they all proceed together in launch-chain mode; a device that saw overlapping evaluations
-  // in the last two seconds stays in launch-chain mode.  LKGPU_WAVE_ALWAYS=1 / LKGPU_STEP_TRSV=1 override.
+  // Evaluations of different handles on one device.  Measured on B200 (tools/diag_concurrent2.py, n = 5000, d = 20,
+  // every handle compared bit for bit with a lone one): when the grids of 2-8 handles are resident together, the
+  // TMA-fed kernels occasionally produce a wrong tile -- a warp of the DMMA kernel or of the wavefront sweep kernel
+  // contributes one pipeline stage of stale operand data (relative errors 1e-6..1e-2 in the gradient, rarely the
+  // value).  Writer-side fences (common.cuh), uncached global loads (build.py), host-separated TRTRI launches,
+  // launch-chain sweeps and tensor maps in device memory took the rate from 2-3 % of the evaluations to 0.03 % (4
+  // handles) .. 0.5 % (8 handles), not to zero, and the mechanism is not understood; a lone handle has never
+  // produced a deviating evaluation.  Therefore:
+  //  * default: evaluations are EXCLUSIVE per device -- handles queue at this gate, their host work still overlaps --
+  //    and use the wavefront sweeps;
+  //  * handles flagged by lkgpu_set_concurrent overlap with each other (launch-chain sweeps, host-separated TRTRI
+  //    launches): the throughput mode for many mid-size factorisations, with the soft-error rate above.
   bool chain_mode = false;
-  bool concurrent_flag = false;  // lkgpu_set_concurrent: this handle is one of several evaluating at the same time
+  bool concurrent_flag = false;  // lkgpu_set_concurrent
+  int gate_depth = 0;  // the gate is re-entrant per handle (append -> restore)
   struct SweepGate {
     Engine& e;
-    bool wave = false;
-    explicit SweepGate(Engine& e_) : e(e_) {
+    bool shared;
+    bool outer;
+    explicit SweepGate(Engine& e_) : e(e_), shared(e_.concurrent_flag), outer(e_.gate_depth++ == 0) {
+      if (!outer) return;
       DeviceGate& g = g_gate[e.device & 63];
       std::unique_lock<std::mutex> lk(g.m);
-      const auto now = std::chrono::steady_clock::now();
-      if (g.wave_active > 0) {
-        ++g.waiting;
-        g.last_multi = now;
-        g.cv.wait(lk, [&] { return g.wave_active == 0; });
-        --g.waiting;
+      if (shared) {
+        g.cv.wait(lk, [&] { return !g.exclusive_active && g.exclusive_waiting == 0; });
+        ++g.shared_active;
+      } else {
+        ++g.exclusive_waiting;
+        g.cv.wait(lk, [&] { return !g.exclusive_active && g.shared_active == 0; });
+        --g.exclusive_waiting;
+        g.exclusive_active = true;
       }
-      ++g.active;
-      const bool recent_multi = g.last_multi.time_since_epoch().count() != 0 &&
-                                std::chrono::steady_clock::now() - g.last_multi < std::chrono::seconds(2);
-      if (g.active > 1 || g.waiting > 0) g.last_multi = std::chrono::steady_clock::now();
-      wave = e.wave_always || (!e.concurrent_flag && g.active == 1 && g.waiting == 0 && !recent_multi);
-      if (wave && !e.wave_always) g.wave_active = 1;
-      e.chain_mode = !wave;
+      e.chain_mode = shared && !e.wave_always;
     }
     ~SweepGate() {
+      --e.gate_depth;
+      if (!outer) return;
       DeviceGate& g = g_gate[e.device & 63];
       {
         std::lock_guard<std::mutex> lk(g.m);
-        --g.active;
-        if (wave && !e.wave_always) g.wave_active = 0;
+        if (shared) --g.shared_active;
+        else g.exclusive_active = false;
       }
       g.cv.notify_all();
     }
@@ -1455,6 +1484,7 @@ struct Engine {
   // ---- exports ----
   void export_mat(int which, double* dst) {
     CUDA_CHECK(cudaSetDevice(device));
+    SweepGate gate(*this);
     if (!have_model) throw LkError{"lkgpu_export: no evaluation has been run on this handle"};
     auto copy_square = [&](const double* src) {
       CUDA_CHECK(cudaMemcpy2D(dst, (size_t)n * 8, src, (size_t)ld * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost));
@@ -1520,6 +1550,7 @@ struct Engine {
   // ---- sigma2 bounds of NoiseModel::Heterogeneous (f2; Kriging.cpp:1784-1797): variogram.cuh ----
   double sigma2_variogram() {
     CUDA_CHECK(cudaSetDevice(device));
+    SweepGate gate(*this);
     const int t = (n + PT - 1) / PT;
     const int ntiles = t * (t + 1) / 2;
     const int grid = std::min(ntiles, 2 * sm_count);
@@ -1590,6 +1621,7 @@ struct Engine {
   // ---- theta bounds (a8) ----
   void theta_bounds(double lo_f, double up_f, int heuristic, double* lower, double* upper) {
     CUDA_CHECK(cudaSetDevice(device));
+    SweepGate gate(*this);
     launches += 1;
     col_minmax_kernel<<<d, 256, 0, s_main>>>(dX, n, dscal + SC_BOUNDS, dscal + SC_BOUNDS + LK_MAX_D);
     CUDA_CHECK(cudaMemcpyAsync(hpin, dscal + SC_BOUNDS, 2 * LK_MAX_D * 8, cudaMemcpyDeviceToHost, s_main));

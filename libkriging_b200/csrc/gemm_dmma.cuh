@@ -161,8 +161,7 @@ __device__ __forceinline__ void load_frags(const uint32_t (&r)[4], double* out) 
 
 template <bool MS_KMAJ, bool NS_KMAJ>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constant__ CUtensorMap tmapN,
-                 const GemmArgs args) {
+gemm_dmma_kernel(const CUtensorMap* tmapM, const CUtensorMap* tmapN, const GemmArgs args) {  // maps in device memory
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms are 1024 bytes: align the ring.
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -198,8 +197,8 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constan
   bool p_live = false;
   TileDesc p_td = {0, 0, 0, 0};
   if (is_producer) {
-    tma_prefetch_desc(&tmapM);
-    tma_prefetch_desc(&tmapN);
+    tma_prefetch_desc(tmapM);
+    tma_prefetch_desc(tmapN);
     p_live = p_tile < args.ntiles;
     if (p_live) {
       p_td = gemm_get_tile(args, p_tile);
@@ -214,16 +213,16 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constan
     mbar_arrive_expect_tx(&full_bar[p_stage], STAGE_BYTES);
     if (NS_KMAJ) {
 #pragma unroll
-      for (int b = 0; b < TN / 64; ++b) tma_load_2d(sN + b * 8192, &tmapN, &full_bar[p_stage], p_k0, p_td.c_col + 64 * b);
+      for (int b = 0; b < TN / 64; ++b) tma_load_2d(sN + b * 8192, tmapN, &full_bar[p_stage], p_k0, p_td.c_col + 64 * b);
     } else {
 #pragma unroll
-      for (int b = 0; b < TN / 16; ++b) tma_load_2d(sN + b * 2048, &tmapN, &full_bar[p_stage], p_td.c_col + 16 * b, p_k0);
+      for (int b = 0; b < TN / 16; ++b) tma_load_2d(sN + b * 2048, tmapN, &full_bar[p_stage], p_td.c_col + 16 * b, p_k0);
     }
     if (MS_KMAJ) {
-      tma_load_2d(sM, &tmapM, &full_bar[p_stage], p_k0, p_td.c_row);
+      tma_load_2d(sM, tmapM, &full_bar[p_stage], p_k0, p_td.c_row);
     } else {
 #pragma unroll
-      for (int b = 0; b < TM / 16; ++b) tma_load_2d(sM + b * 2048, &tmapM, &full_bar[p_stage], p_td.c_row + 16 * b, p_k0);
+      for (int b = 0; b < TM / 16; ++b) tma_load_2d(sM + b * 2048, tmapM, &full_bar[p_stage], p_td.c_row + 16 * b, p_k0);
     }
     if (++p_stage == GSTAGES) {
       p_stage = 0;

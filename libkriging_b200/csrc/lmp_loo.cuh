@@ -328,7 +328,7 @@ void Engine::loo_finish(int want_grad) {
   if (!Q1) {
     Q1 = dalloc<double>((size_t)N * N);
     Q2 = dalloc<double>((size_t)N * N);
-    mapQ1 = {make_map(Q1, N, N, ld, 16, 16), make_map(Q1, N, N, ld, 16, 64)};
+    mapQ1 = maps_of(Q1, false);
   }
   // v = Bm (e.s)
   launches += 3;

@@ -56,7 +56,7 @@ __device__ __forceinline__ void bar_sync_compute() {
 // ctl[0] = ticket counter, ctl[1 + i] = flag of row block i (zeroed by the host before each launch).
 template <bool BWD, int NQ>
 __global__ void __launch_bounds__(WAVE_THREADS, 1)
-trsv_wave_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constant__ CUtensorMap tmapW,
+trsv_wave_kernel(const CUtensorMap* tmapL, const CUtensorMap* tmapW,  // tensor maps in device memory
                  double* __restrict__ B, long long ldb, int nrhs, int nb, int* __restrict__ ctl) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,8 +78,8 @@ trsv_wave_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constan
   }
   __syncthreads();
   if (producer && lane == 0) {
-    tma_prefetch_desc(&tmapL);
-    tma_prefetch_desc(&tmapW);
+    tma_prefetch_desc(tmapL);
+    tma_prefetch_desc(tmapW);
   }
   int* flags = ctl + 1;
   int stage = 0;
@@ -100,7 +100,7 @@ trsv_wave_kernel(const __grid_constant__ CUtensorMap tmapL, const __grid_constan
         for (int tq = 0; tq < ntiles; ++tq) {
           const bool diag = (tq == ntiles - 1);
           const int j = BWD ? (nb - 1 - tq) : tq;  // for the last tile j == i
-          const CUtensorMap* map = diag ? &tmapW : &tmapL;
+          const CUtensorMap* map = diag ? tmapW : tmapL;
           for (int s = 0; s < WAVE_SUBTILES; ++s) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* dst = ring + stage * WAVE_STAGE_BYTES;

@@ -465,10 +465,10 @@ class Kriging:
             # Batched-occupancy path (BASELINE cfg 5, SURVEY.md §8b "several handles per device on separate
             # streams"): a mid-size factorisation cannot fill 148 SMs (its panel chain is latency-bound), so this
             # rank's starts run concurrently, one engine handle (own workspaces, own streams) and one host thread
-            # each.  Evaluations are deterministic (fixed-order reductions), so every start's trajectory is
-            # reproducible bit for bit and equals the sequential loop's up to the rounding of the triangular sweeps
-            # (overlapping evaluations use the launch-chain sweep kernels: engine.cu, SweepGate); the argmin below
-            # is still taken in start order.
+            # each, flagged by lkgpu_set_concurrent so that their evaluations overlap.  Each start's trajectory equals
+            # the sequential loop's up to the rounding of the triangular sweeps (launch-chain kernels here) and the
+            # soft-error rate of overlapping evaluations (engine.cu, SweepGate); the argmin below is still taken in
+            # start order and the committed model is rebuilt by one exclusive evaluation.
             import queue
             from concurrent.futures import ThreadPoolExecutor
             pool_be = queue.SimpleQueue()
@@ -675,15 +675,17 @@ class Kriging:
 
     # ---- helpers ----
     def _concurrency(self, n_starts, n):
-        """Number of engine handles this process runs concurrently for its multistart rows.  Explicit:
-        Kriging(..., concurrent_starts=K) or LKGPU_CONCURRENT_STARTS; automatic: up to 8 for n <= 8192 (a
-        factorisation that size leaves most SMs idle), 1 above, limited by free device memory."""
+        """Number of engine handles this process runs with OVERLAPPING evaluations for its multistart rows.
+        Explicit only: Kriging(..., concurrent_starts=K) or LKGPU_CONCURRENT_STARTS=K (K = 4 is the measured sweet
+        spot for n <= 8192, where one factorisation leaves most SMs idle), limited by free device memory.  Default 1:
+        overlapping evaluations are the throughput mode with the documented soft-error rate ("Concurrent
+        handles"; include/lkgpu.h, lkgpu_set_concurrent), a sequential fit is exact."""
         import os
         want = self._concurrent_starts
         if want is None and os.environ.get("LKGPU_CONCURRENT_STARTS"):
             want = int(os.environ["LKGPU_CONCURRENT_STARTS"])
         if want is None:
-            want = 8 if n <= 8192 else 1
+            want = 1
         want = max(1, min(int(want), n_starts))
         if want > 1 and hasattr(self._backend, "max_handles"):
             want = max(1, min(want, self._backend.max_handles()))

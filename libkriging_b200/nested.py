@@ -6,9 +6,9 @@ per group, "kept sequential for now"), then replaces their hyper-parameters by a
 every sub-model in closed form (unify_hyperparameters, :277-331).  A sub-model is a mid-size factorisation
 (n / p rows) whose panel chain is latency-bound and cannot fill 148 SMs: here the p fits run concurrently, one engine
 handle (own workspaces, own CUDA streams) and one host thread per fit in flight -- the same batched-occupancy
-mechanism as the concurrent multistart rows of Kriging.fit (BASELINE cfg 5).  Evaluations are deterministic, so every
-sub-model is reproducible bit for bit and is the one a sequential loop produces up to the rounding of the triangular
-sweeps (overlapping evaluations use the launch-chain sweep kernels: engine.cu, SweepGate).  Across GPUs the groups shard like multistart rows
+mechanism as the concurrent multistart rows of Kriging.fit (BASELINE cfg 5).  Every sub-model is the one a sequential loop produces up to
+the rounding of the triangular sweeps and the soft-error rate of overlapping evaluations (engine.cu, SweepGate;
+DESIGN.md "Concurrent handles"): `concurrent=1` gives the exact sequential loop.  Across GPUs the groups shard like multistart rows
 (group g on rank g mod world); only the fitted hyper-parameters (d + 2 doubles per group) are exchanged.
 
 Out of scope (reference control plane): the k-means partition (arma::kmeans with arma's own RNG), the PoE / BCM /
@@ -55,7 +55,7 @@ def fit_submodels(y, X, groups, kernel, regmodel="constant", optim="BFGS", objec
     mine = list(range(len(groups))) if comm is None else comm.my_starts(len(groups))
     dev = device if device is not None else (comm.device if comm is not None else 0)
     if concurrent is None:
-        concurrent = 8
+        concurrent = 4
     concurrent = max(1, min(int(concurrent), len(mine) or 1))
 
     def fit_one(g):

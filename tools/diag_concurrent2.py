@@ -11,12 +11,14 @@ from tests.util import synth  # noqa: E402
 
 n, d = int(sys.argv[1]) if len(sys.argv) > 1 else 5000, 20
 nthreads = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+FLAG = os.environ.get("DIAG_FLAG", "1") == "1"   # 1: handles flagged by lkgpu_set_concurrent (overlapping evaluations)
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 X, y, _ = synth(n, d, 505, "smooth")
 F = np.ones((n, 1))
 thetas = [np.full(d, 1.0) * (1 + 0.1 * k) for k in range(3)]
 
-with _capi.Engine(X, y, F, kernel="gauss") as e, _capi.Engine(X[:200], y[:200], F[:200], kernel="gauss") as _idle:
+with _capi.Engine(X, y, F, kernel="gauss") as e:
+    e.set_concurrent(FLAG)  # the reference takes the kernels the concurrent handles take: bit-for-bit comparison
     ref = []
     for th in thetas:
         v, g = e.objective("LL", th, True)
@@ -26,6 +28,8 @@ with _capi.Engine(X, y, F, kernel="gauss") as e, _capi.Engine(X[:200], y[:200], 
     print("sequential repeat identical:", v2 == ref[0][0] and np.array_equal(g2, ref[0][1]), flush=True)
 
 engines = [_capi.Engine(X, y, F, kernel="gauss") for _ in range(nthreads)]
+for e in engines:
+    e.set_concurrent(FLAG)
 bad = []
 lock = threading.Lock()
 
