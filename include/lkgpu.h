@@ -181,11 +181,11 @@ void* lkgpu_get_stream(void* handle);
 int lkgpu_probe_fp64_peak(int device, int mode, double* tflops);
 
 /* Evaluations of different handles on one device are exclusive by default: they queue, and only their host work
- * overlaps.  Handles flagged here overlap with each other (one per multistart row in flight, BASELINE cfg 5; one per
- * NestedKriging sub-model): the throughput mode for many mid-size factorisations.  Known issue, measured on B200 and
- * documented in DESIGN.md ("Concurrent handles"): with the grids of several handles resident together an evaluation
- * has a 0.03 % (4 handles) .. 0.5 % (8 handles) chance of a tile computed from stale operand data (relative error
- * 1e-6 .. 1e-2 in the gradient); a lone or exclusive evaluation has never shown it. */
+ * overlaps (results are those of a lone handle, bit for bit).  Handles flagged here overlap with each other (one per
+ * multistart row in flight, BASELINE cfg 5; one per NestedKriging sub-model): the throughput mode for many mid-size
+ * factorisations.  The default is conservative for historical reasons ("The ring release, and concurrent
+ * handles"): the bug that made overlapping evaluations deviate is fixed -- 0 deviations in 2400 overlapping
+ * evaluations since -- but the policy has not been re-validated for removal yet. */
 int lkgpu_set_concurrent(void* handle, int flag);
 
 /* Free / total bytes of device memory: the host sizes the number of concurrent handles (one per

@@ -34,10 +34,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            # Global loads bypass the per-SM caches: default loads as ld.global.cg (-dlcm=cg) and no ld.global.nc
            # (which `const T* __restrict__` kernel parameters would turn into; -D__restrict__= drops the
-           # qualifier).  Measured on B200 with several handles evaluating concurrently on one GPU: a kernel could
-           # read lines that an earlier kernel of its own stream had cached on that SM before a later kernel rewrote
-           # them (stale R^-1 / vectors in ~0.5 % of the evaluations; never with one handle).  Every such buffer is
-           # streamed once per kernel, so L1 gives nothing here anyway.
+           # qualifier).  Defensive, from the hunt for the deviations of overlapping evaluations ("The ring
+           # release, and concurrent handles"); every such buffer is streamed once per kernel, so L1 gives nothing here.
            "-Xptxas", "-dlcm=cg", "-D__restrict__=",
            "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
            "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]

@@ -23,10 +23,9 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // Writer-side fence for global data that a LATER kernel reads through TMA (async proxy): make this thread's generic-
-// proxy stores visible at gpu scope and order them before async-proxy accesses.  Measured on B200: with several
-// handles running concurrently on one GPU (other grids resident between the producing and the consuming kernel),
-// a TMA load in the next kernel of the same stream could return data from before the previous kernel's last
-// epilogue stores (~1 % of the evaluations; never with a single handle); with this fence after the stores, never.
+// proxy stores visible at gpu scope and order them before async-proxy accesses.  Defensive: it was introduced while
+// hunting the deviations of overlapping evaluations, whose cause turned out to be the ring-slot release (gemm_dmma.cuh);
+// kept until its removal has been validated on the device ("The ring release, and concurrent handles").
 __device__ __forceinline__ void fence_writes_for_tma() {
   __threadfence();
   fence_proxy_async();

@@ -725,6 +725,7 @@ struct Engine {
   void gemm(int layout, const MatMaps& mM, const double* Mbuf, const MatMaps& mN, const double* Nbuf, GemmArgs args,
             cudaStream_t st, bool persistent) {
     if (args.ntiles <= 0) return;
+    args.sched_fence = 0;
     ++launches;
     if (debug_simple) {
       int grid = std::min(args.ntiles, 4 * sm_count);
@@ -959,11 +960,8 @@ struct Engine {
       a.epilogue = EPI_SETNEG;
       a.table = trtri_tables + lv.off2;
       a.ntiles = (int)lv.n2;
-      // Overlapping evaluations: the host waits for each level's first product before launching the second.
-      // TRTRI is the one place where a kernel consumes, through TMA and within microseconds, what the previous
-      // kernel stored; with several handles in flight a stale 32-byte sector was still read there about once in
-      // 2000 evaluations even with the writer-side fences (never with host-separated launches, never with one
-      // handle).  16 waits of ~10 us per evaluation.
+      // Overlapping evaluations: the host waits for each level's first product before launching the second (a
+      // measure from before the ring-release fix, see SweepGate; 16 waits of ~10 us per evaluation).
       if (chain_mode) CUDA_CHECK(cudaStreamSynchronize(s_main));
       gemm(1, mapW, W, mapV, V, a, s_main, true);
       if (chain_mode) CUDA_CHECK(cudaStreamSynchronize(s_main));
@@ -998,29 +996,26 @@ struct Engine {
       const CUtensorMap* mL = BWD ? mapA.wb : mapA.wf;
       const CUtensorMap* mW = BWD ? mapW.wb : mapW.wf;
       if (nq == 1)
-        trsv_wave_kernel<BWD, 1><<<grid, WAVE_THREADS, wave_smem_bytes(1), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl);
+        trsv_wave_kernel<BWD, 1><<<grid, WAVE_THREADS, wave_smem_bytes(1), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, 0);
       else if (nq == 2)
-        trsv_wave_kernel<BWD, 2><<<grid, WAVE_THREADS, wave_smem_bytes(2), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl);
+        trsv_wave_kernel<BWD, 2><<<grid, WAVE_THREADS, wave_smem_bytes(2), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, 0);
       else if (nq <= 4)
-        trsv_wave_kernel<BWD, 4><<<grid, WAVE_THREADS, wave_smem_bytes(4), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl);
+        trsv_wave_kernel<BWD, 4><<<grid, WAVE_THREADS, wave_smem_bytes(4), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, 0);
       else
-        trsv_wave_kernel<BWD, 8><<<grid, WAVE_THREADS, wave_smem_bytes(8), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl);
+        trsv_wave_kernel<BWD, 8><<<grid, WAVE_THREADS, wave_smem_bytes(8), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, 0);
       CUDA_CHECK(cudaGetLastError());
     }
   }
   // ---- triangular sweeps (a5): one persistent wavefront kernel per sweep (trsv_wave.cuh) ----
-  // Evaluations of different handles on one device.  Measured on B200 (tools/diag_concurrent2.py, n = 5000, d = 20,
-  // every handle compared bit for bit with a lone one): when the grids of 2-8 handles are resident together, the
-  // TMA-fed kernels occasionally produce a wrong tile -- a warp of the DMMA kernel or of the wavefront sweep kernel
-  // contributes one pipeline stage of stale operand data (relative errors 1e-6..1e-2 in the gradient, rarely the
-  // value).  Writer-side fences (common.cuh), uncached global loads (build.py), host-separated TRTRI launches,
-  // launch-chain sweeps and tensor maps in device memory took the rate from 2-3 % of the evaluations to 0.03 % (4
-  // handles) .. 0.5 % (8 handles), not to zero, and the mechanism is not understood; a lone handle has never
-  // produced a deviating evaluation.  Therefore:
+  // Evaluations of different handles on one device.  History ("The ring release, and concurrent handles"):
+  // with the grids of several handles resident together 2-3 % of the evaluations used to deviate; the cause was the
+  // ring-slot release being scheduled ahead of the stage's last DMMAs (gemm_dmma.cuh / trsv_wave.cuh, fixed: 0
+  // deviations in 2400 overlapping evaluations since).  The conservative policy adopted during the hunt is kept until
+  // its removal has been validated:
   //  * default: evaluations are EXCLUSIVE per device -- handles queue at this gate, their host work still overlaps --
   //    and use the wavefront sweeps;
   //  * handles flagged by lkgpu_set_concurrent overlap with each other (launch-chain sweeps, host-separated TRTRI
-  //    launches): the throughput mode for many mid-size factorisations, with the soft-error rate above.
+  //    launches): the throughput mode for many mid-size factorisations.
   bool chain_mode = false;
   bool concurrent_flag = false;  // lkgpu_set_concurrent
   int gate_depth = 0;  // the gate is re-entrant per handle (append -> restore)

@@ -62,6 +62,9 @@ struct GemmArgs {
   // attempt: once a panel has found a non-positive pivot (info != 0) the attempt is discarded by safe_chol_lower's
   // ladder (LinearAlgebra.cpp:66-90), so the rest of its trailing updates is skipped.
   const int* abort_flag;
+  // Always 0.  It guards a fence in front of the ring's release (see the main loop): never executed, but as a
+  // potential fence it keeps ptxas from hoisting the release above the last DMMAs of the stage.
+  int sched_fence;
 };
 
 __device__ __forceinline__ TileDesc gemm_get_tile(const GemmArgs& a, int id) {
@@ -303,6 +306,15 @@ gemm_dmma_kernel(const CUtensorMap* tmapM, const CUtensorMap* tmapN, const GemmA
           for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[s & 1][i], b[s & 1][j]);
       }
       __syncwarp();
+      // Release of the ring slot.  It must not be scheduled before the LAST DMMAs of the stage: those consume every
+      // register the stage's LDS filled, so once they have issued all the warp's shared-memory reads of the slot are
+      // complete.  Without the (never taken) fence below, ptxas 12.9 hoisted the SYNCS.ARRIVE to two instructions
+      // after the last LDS *issue* -- legal for lane 0's own loads, but the arrive of lane 0 releases the slot for all
+      // 32 lanes, and when shared-memory traffic is heavy (TMA bursts after a memory backlog) it overtook loads that
+      // were still queued: the refill landed first and one warp computed a stage from the next tile's operands.
+      // Found with tools/diag_foreign.py (95 % of the evaluations deviating next to a bandwidth-bound kernel on
+      // another stream; 0.03-3 % with several handles); tests/test_abi.py checks the SASS order.
+      if (args.sched_fence) fence_proxy_async();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
       if (++stage == GSTAGES) {
         stage = 0;

@@ -57,7 +57,7 @@ __device__ __forceinline__ void bar_sync_compute() {
 template <bool BWD, int NQ>
 __global__ void __launch_bounds__(WAVE_THREADS, 1)
 trsv_wave_kernel(const CUtensorMap* tmapL, const CUtensorMap* tmapW,  // tensor maps in device memory
-                 double* __restrict__ B, long long ldb, int nrhs, int nb, int* __restrict__ ctl) {
+                 double* __restrict__ B, long long ldb, int nrhs, int nb, int* __restrict__ ctl, int sched_fence) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   double* vec = reinterpret_cast<double*>(ring + WAVE_STAGES * WAVE_STAGE_BYTES);  // [NQ][128] current z_j / t
@@ -187,6 +187,9 @@ trsv_wave_kernel(const CUtensorMap* tmapL, const CUtensorMap* tmapW,  // tensor 
           }
         }
         __syncwarp();
+        // release of the ring slot: kept behind the last FMAs of the sub-tile by a never-taken fence (sched_fence is
+        // always 0), for the reason given at the same place in gemm_dmma.cuh
+        if (sched_fence) fence_proxy_async();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
         if (++stage == WAVE_STAGES) {
           stage = 0;

@@ -466,9 +466,9 @@ class Kriging:
             # streams"): a mid-size factorisation cannot fill 148 SMs (its panel chain is latency-bound), so this
             # rank's starts run concurrently, one engine handle (own workspaces, own streams) and one host thread
             # each, flagged by lkgpu_set_concurrent so that their evaluations overlap.  Each start's trajectory equals
-            # the sequential loop's up to the rounding of the triangular sweeps (launch-chain kernels here) and the
-            # soft-error rate of overlapping evaluations (engine.cu, SweepGate); the argmin below is still taken in
-            # start order and the committed model is rebuilt by one exclusive evaluation.
+            # the sequential loop's up to the rounding of the triangular sweeps (launch-chain kernels here; engine.cu,
+            # SweepGate); the argmin below is still taken in start order and the committed model is rebuilt by one
+            # exclusive evaluation.
             import queue
             from concurrent.futures import ThreadPoolExecutor
             pool_be = queue.SimpleQueue()
@@ -677,9 +677,8 @@ class Kriging:
     def _concurrency(self, n_starts, n):
         """Number of engine handles this process runs with OVERLAPPING evaluations for its multistart rows.
         Explicit only: Kriging(..., concurrent_starts=K) or LKGPU_CONCURRENT_STARTS=K (K = 4 is the measured sweet
-        spot for n <= 8192, where one factorisation leaves most SMs idle), limited by free device memory.  Default 1:
-        overlapping evaluations are the throughput mode with the documented soft-error rate ("Concurrent
-        handles"; include/lkgpu.h, lkgpu_set_concurrent), a sequential fit is exact."""
+        spot for n <= 8192, where one factorisation leaves most SMs idle), limited by free device memory.  Default 1
+        (conservative, see DESIGN.md "The ring release, and concurrent handles" and lkgpu_set_concurrent)."""
         import os
         want = self._concurrent_starts
         if want is None and os.environ.get("LKGPU_CONCURRENT_STARTS"):

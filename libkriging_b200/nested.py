@@ -7,8 +7,8 @@ every sub-model in closed form (unify_hyperparameters, :277-331).  A sub-model i
 (n / p rows) whose panel chain is latency-bound and cannot fill 148 SMs: here the p fits run concurrently, one engine
 handle (own workspaces, own CUDA streams) and one host thread per fit in flight -- the same batched-occupancy
 mechanism as the concurrent multistart rows of Kriging.fit (BASELINE cfg 5).  Every sub-model is the one a sequential loop produces up to
-the rounding of the triangular sweeps and the soft-error rate of overlapping evaluations (engine.cu, SweepGate;
-DESIGN.md "Concurrent handles"): `concurrent=1` gives the exact sequential loop.  Across GPUs the groups shard like multistart rows
+the rounding of the triangular sweeps (overlapping evaluations use the launch-chain sweep kernels: engine.cu,
+SweepGate); `concurrent=1` gives the exact sequential loop.  Across GPUs the groups shard like multistart rows
 (group g on rank g mod world); only the fitted hyper-parameters (d + 2 doubles per group) are exchanged.
 
 Out of scope (reference control plane): the k-means partition (arma::kmeans with arma's own RNG), the PoE / BCM /

@@ -121,8 +121,7 @@ def test_cfg5_gauss_n5000_d20_vs_oracle_and_concurrent_starts(capi):
         k.close()
     a, b, c = fits
     # several handles with overlapping evaluations: the sequential loop's fit up to the rounding of the triangular
-    # sweeps (launch-chain kernels when evaluations overlap) and the soft-error rate documented in DESIGN.md
-    # ("Concurrent handles") -- which is why these comparisons carry a tolerance and not np.array_equal
+    # sweeps (launch-chain kernels when evaluations overlap; DESIGN.md, "The ring release, and concurrent handles")
     for u, v in ((a, b), (b, c)):
         assert u[0] == v[0]
         assert relerr(u[1], v[1]) < 1e-6 and relerr(u[3], v[3]) < 1e-3 and relerr(u[4], v[4]) < 1e-3

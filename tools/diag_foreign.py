@@ -54,7 +54,9 @@ def foreign():
 
 
 with _capi.Engine(X, y, F, kernel="gauss") as e:
-    e.set_concurrent(True)   # launch-chain sweeps; and the gate lets the foreign engine overlap
+    # DIAG_FLAG=1 (default): flagged handle = launch-chain sweeps, and the gate lets the foreign engine overlap;
+    # DIAG_FLAG=0: the default exclusive mode with the wavefront sweep kernel
+    e.set_concurrent(os.environ.get("DIAG_FLAG", "1") == "1")
     ref = []
     for th in thetas:
         v, g = e.objective("LL", th, True)
