@@ -215,6 +215,10 @@ struct Engine {
   bool debug_simple = false;
   bool use_lookahead = true;
   bool use_step_trsv = false;
+  // Host-side switches for validating the removal of the defensive measures one at a time (tools/validate_relax.sh):
+  bool overlap_default = false;   // LKGPU_OVERLAP_DEFAULT=1: unflagged handles overlap too (no exclusive queue)
+  bool trtri_nosync = false;      // LKGPU_TRTRI_NOSYNC=1: no host wait between TRTRI's launches for overlapping evaluations
+  bool wave_when_shared = false;  // LKGPU_WAVE_WHEN_SHARED=1: overlapping evaluations use the wavefront sweeps
   bool l2_order = true;  // LKGPU_NO_L2_ORDER=1: tile tables sorted by k-length only (the r01c order)
   bool wave_always = false;
   int wave_grid_cap = 0;  // LKGPU_WAVE_GRID=k: at most k CTAs per sweep (fault localisation)
@@ -370,6 +374,9 @@ struct Engine {
     use_lookahead = !(nla && nla[0] == '1');
     if (const char* op = getenv("LKGPU_OUTER_PANELS")) outer_panels = std::max(1, std::min(16, atoi(op)));
     if (const char* wg = getenv("LKGPU_WAVE_GRID")) wave_grid_cap = atoi(wg);
+    if (const char* v = getenv("LKGPU_OVERLAP_DEFAULT")) overlap_default = v[0] == '1';
+    if (const char* v = getenv("LKGPU_TRTRI_NOSYNC")) trtri_nosync = v[0] == '1';
+    if (const char* v = getenv("LKGPU_WAVE_WHEN_SHARED")) wave_when_shared = v[0] == '1';
     if (const char* nlo = getenv("LKGPU_NO_L2_ORDER")) l2_order = !(nlo[0] == '1');
     if (const char* wa = getenv("LKGPU_WAVE_ALWAYS")) wave_always = wa[0] == '1';
     const char* npe = getenv("LKGPU_NO_PERSISTENT");
@@ -962,9 +969,9 @@ struct Engine {
       a.ntiles = (int)lv.n2;
       // Overlapping evaluations: the host waits for each level's first product before launching the second (a
       // measure from before the ring-release fix, see SweepGate; 16 waits of ~10 us per evaluation).
-      if (chain_mode) CUDA_CHECK(cudaStreamSynchronize(s_main));
+      if (sync_trtri) CUDA_CHECK(cudaStreamSynchronize(s_main));
       gemm(1, mapW, W, mapV, V, a, s_main, true);
-      if (chain_mode) CUDA_CHECK(cudaStreamSynchronize(s_main));
+      if (sync_trtri) CUDA_CHECK(cudaStreamSynchronize(s_main));
     }
     have_W = true;
   }
@@ -1017,13 +1024,14 @@ struct Engine {
   //  * handles flagged by lkgpu_set_concurrent overlap with each other (launch-chain sweeps, host-separated TRTRI
   //    launches): the throughput mode for many mid-size factorisations.
   bool chain_mode = false;
+  bool sync_trtri = false;
   bool concurrent_flag = false;  // lkgpu_set_concurrent
   int gate_depth = 0;  // the gate is re-entrant per handle (append -> restore)
   struct SweepGate {
     Engine& e;
     bool shared;
     bool outer;
-    explicit SweepGate(Engine& e_) : e(e_), shared(e_.concurrent_flag), outer(e_.gate_depth++ == 0) {
+    explicit SweepGate(Engine& e_) : e(e_), shared(e_.concurrent_flag || e_.overlap_default), outer(e_.gate_depth++ == 0) {
       if (!outer) return;
       DeviceGate& g = g_gate[e.device & 63];
       std::unique_lock<std::mutex> lk(g.m);
@@ -1036,7 +1044,8 @@ struct Engine {
         --g.exclusive_waiting;
         g.exclusive_active = true;
       }
-      e.chain_mode = shared && !e.wave_always;
+      e.chain_mode = shared && !e.wave_always && !e.wave_when_shared;
+      e.sync_trtri = shared && !e.trtri_nosync;
     }
     ~SweepGate() {
       --e.gate_depth;
