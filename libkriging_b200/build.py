@@ -39,6 +39,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-Xptxas", "-dlcm=cg", "-D__restrict__=",
            "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
            "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    # experiments (tools/validate_relax.sh): LKGPU_BUILD_FLAGS adds flags, LKGPU_BUILD_DROP removes defaults, e.g.
+    #   LKGPU_BUILD_FLAGS="-DLKGPU_NO_WRITER_FENCE" LKGPU_BUILD_DROP="-dlcm=cg -D__restrict__=" python -m libkriging_b200.build --force
+    for drop in os.environ.get("LKGPU_BUILD_DROP", "").split():
+        while drop in cmd:
+            i = cmd.index(drop)
+            if i > 0 and cmd[i - 1] == "-Xptxas":
+                del cmd[i - 1:i + 1]
+            else:
+                del cmd[i]
+    extra = os.environ.get("LKGPU_BUILD_FLAGS", "").split()
+    if extra:
+        cmd[1:1] = extra
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
