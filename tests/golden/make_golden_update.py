@@ -44,6 +44,16 @@ CASES = [
     # a from-scratch factorisation of the same data gives sigma2 = 1771.8 instead of 3534.5.
     dict(name="upd-m52-jitter-n150+9-d3", n0=150, n_u=9, d=3, seed=69, kernel="matern5_2", noise_model="none",
          objective="LL", optim="none", theta0=0.6, dup=6, refits=(False,)),
+    # normalize = true (the update re-uses the model's own centre / scale, Kriging.cpp:2472-2476), a linear trend,
+    # and the two re-fit branches: Nugget (new fit from scratch, :2443-2468) and Heterogeneous with refit (:2645-2658)
+    dict(name="upd-m52-norm-n200+30-d3", n0=200, n_u=30, d=3, seed=71, kernel="matern5_2", noise_model="none",
+         objective="LL", optim="BFGS", theta0=0.6, normalize=True),
+    dict(name="upd-m32-linear-n150+25-d2", n0=150, n_u=25, d=2, seed=72, kernel="matern3_2", noise_model="none",
+         objective="LL", optim="BFGS", theta0=0.5, regmodel="linear"),
+    dict(name="upd-m52-nugget-n150+20-d3", n0=150, n_u=20, d=3, seed=73, kernel="matern5_2", noise_model="nugget",
+         objective="LL", optim="BFGS", theta0=0.6, refits=(True,)),
+    dict(name="upd-m52-hetero-n150+20-d3-bfgs", n0=150, n_u=20, d=3, seed=74, kernel="matern5_2", noise_model="hetero",
+         objective="LL", optim="BFGS", theta0=0.6, sigma2=0.5, refits=(True,)),
     dict(name="upd-m52-jitter-n300+140-d3", n0=300, n_u=140, d=3, seed=70, kernel="matern5_2", noise_model="none",
          objective="LL", optim="none", theta0=0.6, dup=3, refits=(False,)),
 ]
@@ -64,7 +74,8 @@ def main():
                 kw.update(noise=noise[:n0], sigma2=c["sigma2"], est_sigma2=False)
             upd = dict(X=X[n0:], y=y[n0:], refit=refit, noise=noise[n0:] if c["noise_model"] == "hetero" else None)
             r = ref.run(X[:n0], y[:n0], kernel=c["kernel"], noise_model=c["noise_model"], objective=c["objective"],
-                        mode="fit", optim=c["optim"], theta=th0, Xn=Xn, threads=1, update=upd, **kw)
+                        mode="fit", optim=c["optim"], theta=th0, Xn=Xn, threads=1, update=upd,
+                        normalize=c.get("normalize", False), regmodel=c.get("regmodel", "constant"), **kw)
             rec = dict(c, refit=refit, yfun="smooth", theta=r["theta"], sigma2=r["sigma2"], nugget=r["nugget"],
                        beta=r["beta"], LL_at_model=r["LL_at_model"], pred_mean=r["pred_mean"], pred_sd=r["pred_sd"])
             rec.pop("refits", None)

@@ -81,8 +81,9 @@ def test_cpp_host_update_matches_reference(c):
     kw = dict(noise=noise[:n0], sigma2=c["sigma2"], est_sigma2=False) if het else {}
     r = host.run(X[:n0], y[:n0], kernel=c["kernel"], noise_model=c["noise_model"], objective=c["objective"], mode="fit",
                  optim=c["optim"], theta=np.full((1, c["d"]), c["theta0"]), Xn=Xn,
+                 regmodel=c.get("regmodel", "constant"), normalize=c.get("normalize", False),
                  update=dict(X=X[n0:], y=y[n0:], refit=c["refit"], noise=noise[n0:] if het else None), **kw)
-    tol = update_tol(c)
+    tol = update_tol(c, device=True)
     if not c["refit"] and not het:
         assert r["used_block_extension"] == 1
     assert relerr(r["theta"], c["theta"]) < tol

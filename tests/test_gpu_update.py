@@ -161,7 +161,7 @@ def test_update_matches_reference_on_device(c):
     try:
         if not c["refit"] and c["noise_model"] != "hetero":
             assert k._backend.used_block_update
-        check_update_case(k, c, update_tol(c))
+        check_update_case(k, c, update_tol(c, device=True))
     finally:
         k.close()
 
