@@ -219,6 +219,7 @@ struct Engine {
   bool overlap_default = false;   // LKGPU_OVERLAP_DEFAULT=1: unflagged handles overlap too (no exclusive queue)
   bool trtri_nosync = false;      // LKGPU_TRTRI_NOSYNC=1: no host wait between TRTRI's launches for overlapping evaluations
   bool wave_when_shared = false;  // LKGPU_WAVE_WHEN_SHARED=1: overlapping evaluations use the wavefront sweeps
+  int persistent_update_reserve = 0;
   bool l2_order = true;  // LKGPU_NO_L2_ORDER=1: tile tables sorted by k-length only (the r01c order)
   bool wave_always = false;
   int wave_grid_cap = 0;  // LKGPU_WAVE_GRID=k: at most k CTAs per sweep (fault localisation)
@@ -374,6 +375,7 @@ struct Engine {
     use_lookahead = !(nla && nla[0] == '1');
     if (const char* op = getenv("LKGPU_OUTER_PANELS")) outer_panels = std::max(1, std::min(16, atoi(op)));
     if (const char* wg = getenv("LKGPU_WAVE_GRID")) wave_grid_cap = atoi(wg);
+    if (const char* v = getenv("LKGPU_PERSISTENT_UPDATE")) persistent_update_reserve = std::max(0, atoi(v));
     if (const char* v = getenv("LKGPU_OVERLAP_DEFAULT")) overlap_default = v[0] == '1';
     if (const char* v = getenv("LKGPU_TRTRI_NOSYNC")) trtri_nosync = v[0] == '1';
     if (const char* v = getenv("LKGPU_WAVE_WHEN_SHARED")) wave_when_shared = v[0] == '1';
@@ -730,7 +732,7 @@ struct Engine {
   // ---- GEMM launcher ----
   // layout: 0 = NT (both M-major), 1 = NN (M-side M-major, N-side K-major), 2 = TN (both K-major)
   void gemm(int layout, const MatMaps& mM, const double* Mbuf, const MatMaps& mN, const double* Nbuf, GemmArgs args,
-            cudaStream_t st, bool persistent) {
+            cudaStream_t st, bool persistent, int grid_cap = 0) {
     if (args.ntiles <= 0) return;
     args.sched_fence = 0;
     ++launches;
@@ -743,6 +745,7 @@ struct Engine {
       return;
     }
     int grid = (persistent && !no_persistent) ? std::min(args.ntiles, 2 * sm_count) : args.ntiles;
+    if (grid_cap > 0) grid = std::min(grid, grid_cap);
     if (layout == 0)
       gemm_dmma_kernel<false, false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mM.mm, mN.mm, args);
     else if (layout == 1)
@@ -855,7 +858,13 @@ struct Engine {
         gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1, 2 * rem, OB, c0, c1)), s_main, false);
         // ... the rest of the trailing matrix on the low-priority stream
         CUDA_CHECK(cudaStreamWaitEvent(s_upd, ev_panel[J0], 0));
-        gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1 + OB * BLK, 2 * (rem - OB), rem - OB, c0, c1)), s_upd, false);
+        // (experiment for round 2, off by default: LKGPU_PERSISTENT_UPDATE=r runs this update as a persistent grid on
+        //  2 (SMs - r) CTAs -- the run-ahead producer then hides each tile's prologue -- leaving r SMs to the panel chain)
+        if (persistent_update_reserve > 0)
+          gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1 + OB * BLK, 2 * (rem - OB), rem - OB, c0, c1)), s_upd, true,
+               2 * std::max(1, sm_count - persistent_update_reserve));
+        else
+          gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1 + OB * BLK, 2 * (rem - OB), rem - OB, c0, c1)), s_upd, false);
         CUDA_CHECK(cudaEventRecord(ev_upd[J0], s_upd));
         last_upd = J0;
       } else {

@@ -12,3 +12,5 @@ run LKGPU_WAVE_WHEN_SHARED=1 python tools/diag_concurrent2.py 5000 8 40
 run LKGPU_WAVE_WHEN_SHARED=1 LKGPU_TRTRI_NOSYNC=1 python tools/diag_concurrent2.py 5000 8 40
 run LKGPU_WAVE_WHEN_SHARED=1 LKGPU_TRTRI_NOSYNC=1 python tools/diag_foreign.py elementwise 60
 run DIAG_FLAG=0 LKGPU_OVERLAP_DEFAULT=1 LKGPU_WAVE_WHEN_SHARED=1 LKGPU_TRTRI_NOSYNC=1 python tools/diag_concurrent2.py 5000 8 40
+# Cholesky experiment: persistent trailing update with r SMs left to the panel chain
+for r in 0 4 8 12 16; do echo "== LKGPU_PERSISTENT_UPDATE=$r"; LKGPU_PERSISTENT_UPDATE=$r python tools/profile_eval.py 20000 10 3 2>&1 | tail -1 | grep -o "chol.: [0-9.]*"; done
