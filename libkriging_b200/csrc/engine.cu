@@ -194,13 +194,6 @@ __global__ void copy_kernel(double* __restrict__ dst, const double* __restrict__
   fence_writes_for_tma();
 }
 
-__global__ void scale_signs_kernel(double* x, int n, int mode) {
-  // dlacn2 helpers: mode 0: x = sign(x) ; mode 1: altsgn ramp
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (mode == 0) x[i] = (x[i] >= 0.0) ? 1.0 : -1.0;
-}
-
 // dscal slot map (device scalars copied back at the end of an evaluation)
 enum {
   SC_SUMLOG = 0, SC_SSE = 1, SC_DIAG = 4 /*4 slots*/, SC_LOO = 8, SC_NORML = 9, SC_NORMW = 10,
@@ -1099,15 +1092,6 @@ struct Engine {
       }
       CUDA_CHECK(cudaGetLastError());
     }
-  }
-
-  double norm1_lower(const double* M) {
-    launches += 2;
-    tri_colsum_abs_kernel<<<(n * 32 + 255) / 256, 256, 0, s_main>>>(M, ld, n, dcolsum);
-    vec_max_kernel<<<1, 256, 0, s_main>>>(dcolsum, n, dscal + SC_NORML);
-    CUDA_CHECK(cudaMemcpyAsync(hpin, dscal + SC_NORML, 8, cudaMemcpyDeviceToHost, s_main));
-    CUDA_CHECK(cudaStreamSynchronize(s_main));
-    return hpin[0];
   }
 
   // dtrcon('1','L','N') restated: Higham/Hager estimator dlacn2 driven from the host,
