@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblkgpu.so")
+# LKGPU_LIB selects another build of the same library (experiment variants, tools/validate_relax.sh)
+LIB_PATH = os.environ.get("LKGPU_LIB") or os.path.join(HERE, "liblkgpu.so")
 
 KERNELS = {"gauss": 0, "exp": 1, "matern3_2": 2, "matern5_2": 3}
 NOISE = {"none": 0, "nugget": 1, "hetero": 2}

@@ -27,9 +27,15 @@ def needs_build() -> bool:
     return False
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    """Build the library.  `out` (or LKGPU_BUILD_OUT) names another output file: experiment variants next to the
+    product library, selected at run time with LKGPU_LIB (libkriging_b200/_capi.py)."""
+    out = out or os.environ.get("LKGPU_BUILD_OUT")
+    if out:
+        force = True
+    elif not force and not needs_build():
         return LIB
+    lib_out = os.path.abspath(out) if out else LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            # Global loads bypass the per-SM caches: default loads as ld.global.cg (-dlcm=cg) and no ld.global.nc
@@ -38,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            # release, and concurrent handles"); every such buffer is streamed once per kernel, so L1 gives nothing here.
            "-Xptxas", "-dlcm=cg", "-D__restrict__=",
            "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", lib_out] + [os.path.join(CSRC, s) for s in SOURCES]
     # experiments (tools/validate_relax.sh): LKGPU_BUILD_FLAGS adds flags, LKGPU_BUILD_DROP removes defaults, e.g.
     #   LKGPU_BUILD_FLAGS="-DLKGPU_NO_WRITER_FENCE" LKGPU_BUILD_DROP="-dlcm=cg -D__restrict__=" python -m libkriging_b200.build --force
     for drop in os.environ.get("LKGPU_BUILD_DROP", "").split():
@@ -59,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building liblkgpu.so")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":

@@ -22,6 +22,12 @@ __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Consumer-side release fence of a TMA ring slot: orders this thread's generic-proxy accesses to shared memory (the
+// LDS that read the slot) before later async-proxy accesses to it (the TMA refill).  Executed by every lane before
+// the warp-level arrive on the slot's empty barrier; see the main loop of gemm_dmma.cuh.
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 // Writer-side fence for global data that a LATER kernel reads through TMA (async proxy): make this thread's generic-
 // proxy stores visible at gpu scope and order them before async-proxy accesses.  Defensive: it was introduced while
 // hunting the deviations of overlapping evaluations, whose cause turned out to be the ring-slot release (gemm_dmma.cuh);

@@ -27,6 +27,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef LKGPU_RING_RELEASE
+#define LKGPU_RING_RELEASE 1  // 1: real per-lane proxy fence before the ring-slot release; 0: round 1's never-taken fence
+#endif
+
 namespace lk {
 
 constexpr int TM = 64;       // C rows per tile
@@ -62,8 +66,7 @@ struct GemmArgs {
   // attempt: once a panel has found a non-positive pivot (info != 0) the attempt is discarded by safe_chol_lower's
   // ladder (LinearAlgebra.cpp:66-90), so the rest of its trailing updates is skipped.
   const int* abort_flag;
-  // Always 0.  It guards a fence in front of the ring's release (see the main loop): never executed, but as a
-  // potential fence it keeps ptxas from hoisting the release above the last DMMAs of the stage.
+  // Always 0; only read by the LKGPU_RING_RELEASE=0 build (round 1's never-taken fence, kept for A/B timing).
   int sched_fence;
 };
 
@@ -305,16 +308,22 @@ gemm_dmma_kernel(const CUtensorMap* tmapM, const CUtensorMap* tmapN, const GemmA
 #pragma unroll
           for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[s & 1][i], b[s & 1][j]);
       }
+      // Release of the ring slot -- ordered by construction.  The slot is refilled by TMA (async proxy) while it was
+      // read by LDS (generic proxy): every lane first executes fence.proxy.async.shared::cta, which orders ITS reads
+      // of the slot before later async-proxy accesses (and, as a memory fence, cannot complete before those loads
+      // have), the lanes then meet at bar.warp.sync, and only then lane 0 arrives (release) on the empty barrier that
+      // the producer acquires before issuing the refill.  History: without any fence ptxas 12.9 placed the
+      // SYNCS.ARRIVE two instructions after the last LDS *issue*, ahead of the DMMAs consuming those loads, and
+      // under heavy shared-memory traffic the refill overtook loads still queued (profiles/r01c_ring_release.md;
+      // found with tools/diag_foreign.py).  Round 1 pinned the arrive with a never-taken fence -- a scheduling
+      // trick; LKGPU_RING_RELEASE=0 still builds that variant for A/B timing.  tests/test_abi.py checks the SASS.
+#if LKGPU_RING_RELEASE
+      fence_proxy_async_smem();
       __syncwarp();
-      // Release of the ring slot.  It must not be scheduled before the LAST DMMAs of the stage: those consume every
-      // register the stage's LDS filled, so once they have issued all the warp's shared-memory reads of the slot are
-      // complete.  Without the (never taken) fence below, ptxas 12.9 hoisted the SYNCS.ARRIVE to two instructions
-      // after the last LDS *issue* -- legal for lane 0's own loads, but the arrive of lane 0 releases the slot for all
-      // 32 lanes, and when shared-memory traffic is heavy (TMA bursts after a memory backlog) it overtook loads that
-      // were still queued: the refill landed first and one warp computed a stage from the next tile's operands.
-      // Found with tools/diag_foreign.py (95 % of the evaluations deviating next to a bandwidth-bound kernel on
-      // another stream; 0.03-3 % with several handles); tests/test_abi.py checks the SASS order.
+#else
+      __syncwarp();
       if (args.sched_fence) fence_proxy_async();
+#endif
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
       if (++stage == GSTAGES) {
         stage = 0;

@@ -19,6 +19,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef LKGPU_RING_RELEASE
+#define LKGPU_RING_RELEASE 1
+#endif
+
 namespace lk {
 
 constexpr int WAVE_COMPUTE_THREADS = 256;
@@ -59,7 +63,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1)
 trsv_wave_kernel(const CUtensorMap* tmapL, const CUtensorMap* tmapW,  // tensor maps in device memory
                  double* __restrict__ B, long long ldb, int nrhs, int nb, int* __restrict__ ctl, int sched_fence) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the shared array (not through an integer cast): the compiler keeps
+  // the shared address space, so the tile / vector reads below are LDS, not generic loads.
+  uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   double* vec = reinterpret_cast<double*>(ring + WAVE_STAGES * WAVE_STAGE_BYTES);  // [NQ][128] current z_j / t
   double* part = vec + NQ * 128;                                                   // [2][NQ][128] partials
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + 2 * NQ * 128);
@@ -186,10 +192,14 @@ trsv_wave_kernel(const CUtensorMap* tmapL, const CUtensorMap* tmapW,  // tensor 
             }
           }
         }
+        // release of the ring slot: per-lane proxy fence, warp barrier, then lane 0's arrive (see gemm_dmma.cuh)
+#if LKGPU_RING_RELEASE
+        fence_proxy_async_smem();
         __syncwarp();
-        // release of the ring slot: kept behind the last FMAs of the sub-tile by a never-taken fence (sched_fence is
-        // always 0), for the reason given at the same place in gemm_dmma.cuh
+#else
+        __syncwarp();
         if (sched_fence) fence_proxy_async();
+#endif
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
         if (++stage == WAVE_STAGES) {
           stage = 0;

@@ -48,19 +48,22 @@ def test_no_cpu_fallback_without_device():
         _capi.probe_fp64_peak()
 
 
-def test_ring_release_is_scheduled_after_the_stage_math():
-    """SASS guard for the TMA ring kernels (gemm_dmma_kernel, trsv_wave_kernel): the release of a ring slot
-    (SYNCS.ARRIVE...A1T0 on the empty barrier) must come after the last math instruction that consumes the slot's
-    shared-memory reads.  ptxas 12.9 hoisted it to just after the last LDS issue when nothing stopped it, and under
-    heavy shared-memory traffic the refill then overtook queued loads ("Concurrent handles"); the kernels
-    keep it in place with a never-taken fence.  This test fails if a compiler change undoes that."""
+def test_ring_release_is_ordered_by_a_real_fence():
+    """SASS guard for the TMA ring kernels (gemm_dmma_kernel, trsv_wave_kernel): between the last shared-memory read
+    of a ring slot and the slot's release (SYNCS.ARRIVE...A1T0 on the empty barrier) every lane executes an
+    UNCONDITIONAL memory barrier + async-proxy fence (fence.proxy.async.shared::cta -> MEMBAR.ALL.CTA +
+    FENCE.VIEW.ASYNC.S).  The barrier cannot complete before the warp's LDS have, and the fence orders those
+    generic-proxy reads before the TMA refill (async proxy) that the release allows: the order holds by construction,
+    not by instruction scheduling.  (Round 1 pinned the release behind the stage's DMMAs with a never-taken branch;
+    without anything ptxas 12.9 hoisted it to just after the last LDS *issue* and refills overtook queued loads under
+    heavy shared-memory traffic, profiles/r01c_ring_release.md.)"""
     import shutil
     import subprocess
     from libkriging_b200 import build
-    if shutil.which("cuobjdump") is None:
-        pytest.skip("cuobjdump not available")
+    assert shutil.which("cuobjdump") is not None, "cuobjdump (CUDA toolkit) is required for the SASS guard"
     sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True, check=True).stdout
     seen = 0
+    pred = r"(@!?U?P\d+\s+)?"
     for f in re.split(r"\n\s*Function : ", sass)[1:]:
         name = f.split("\n", 1)[0].strip()
         if "gemm_dmma_kernel" not in name and "trsv_wave_kernel" not in name:
@@ -70,17 +73,20 @@ def test_ring_release_is_scheduled_after_the_stage_math():
         rel = [i for i, t in enumerate(ins) if "SYNCS.ARRIVE.TRANS64.A1T0" in t]
         assert len(rel) == 1, (name, len(rel))
         r = rel[0]
-        # backwards from the release to the consumer's full-barrier wait: the stage's math sits in between ...
+        # the consumer's stage: from its full-barrier wait to the release
         w = max(i for i in range(r) if "SYNCS.PHASECHK" in ins[i])
-        n_math = sum(1 for t in ins[w:r] if re.match(r"(@!?U?P\d+\s+)?" + math, t))
+        seg = ins[w:r]
+        n_math = sum(1 for t in ins[w:] if re.match(pred + math, t))
         assert n_math >= (128 if math == "DMMA" else 16), (name, n_math)
-        assert any("FENCE" in t for t in ins[r - 8:r]), name
-        # ... and none of it after the release, up to the next barrier wait / branch
-        tail = []
-        for t in ins[r + 1:]:
-            if "SYNCS.PHASECHK" in t or re.match(r"(@!?U?P\d+\s+)?BRA", t):
-                break
-            tail.append(t)
-        assert not [t for t in tail if re.match(r"(@!?U?P\d+\s+)?" + math, t)], (name, tail)
+        # every read of the slot is a shared-memory load (no generic loads on the ring) ...
+        assert not [t for t in seg if re.match(pred + r"LD\.E", t) and "STRONG" in t and "0x3" in t], name
+        lds = [i for i, t in enumerate(seg) if re.match(pred + "LDS", t)]
+        assert lds, name
+        after = seg[lds[-1] + 1:]
+        # ... and after the last of them, before the release: an unpredicated barrier + proxy fence, not skippable
+        mb = [i for i, t in enumerate(after) if t.startswith("MEMBAR.ALL")]
+        fv = [i for i, t in enumerate(after) if t.startswith("FENCE.VIEW.ASYNC")]
+        assert mb and fv and mb[0] < fv[0], (name, after)
+        assert not [t for t in after if re.match(pred + r"(BRA|BRX|JMP)", t)], (name, after)
         seen += 1
     assert seen == 11  # 3 GEMM layouts + 8 sweep variants
