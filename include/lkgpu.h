@@ -41,7 +41,8 @@ enum {
   LKGPU_EXPORT_LINV = 7,   /* n*n, L^-1 lower (LOO's KModel::Linv)                           */
   LKGPU_EXPORT_X = 8,      /* n, x = L^-T Estar                                              */
   LKGPU_EXPORT_LOO_ERR = 9,  /* n, errorsLOO (yhat_loo = y - errorsLOO), after a LOO evaluation   */
-  LKGPU_EXPORT_LOO_S2 = 10   /* n, sigma2LOO = 1/diag(B) (unscaled), after a LOO evaluation       */
+  LKGPU_EXPORT_LOO_S2 = 10,  /* n, sigma2LOO = 1/diag(B) (unscaled), after a LOO evaluation       */
+  LKGPU_EXPORT_Z = 11        /* n, m_z: Estar, or ystar - Fstar beta after lkgpu_set_fixed_beta     */
 };
 
 #define LKGPU_N_STAGES 12
@@ -59,7 +60,8 @@ enum {
   LKGPU_ST_TOTAL = 8,   /* whole evaluation, device time        */
   /* counters kept in the spare slots (not times): rungs of safe_chol_lower's ladder rejected ...            */
   LKGPU_CT_REJECT_INFO = 9,   /* ... because the factorisation failed (non-positive pivot; attempt aborted) */
-  LKGPU_CT_REJECT_RCOND = 10  /* ... because rcond_1(L)^2 < min_rcond                                      */
+  LKGPU_CT_REJECT_RCOND = 10, /* ... because rcond_1(L)^2 < min_rcond                                      */
+  LKGPU_CT_RUNGS_SKIPPED = 11 /* rungs the ladder shortcut did not factor (lkgpu_set_ladder_shortcut)      */
 };
 
 typedef struct lkgpu_out {
@@ -123,6 +125,13 @@ int lkgpu_eval(void* handle, int objective, const double* theta, double extra, i
  * Defaults: everything estimated, sigma2 = 1, nugget = 0, alpha = 1. */
 int lkgpu_set_params(void* handle, int est_sigma2, double sigma2, int est_nugget, double nugget, double alpha);
 
+/* m_est_beta == false (Parameters::is_beta_estim = false with beta given, src/lib/Kriging.cpp:1668-1676): the trend
+ * coefficients are fixed by the caller.  The objectives keep using the GLS estimate (src/lib/KrigingImpl.cpp:113-123);
+ * what changes is the committed z = ystar - M beta (src/lib/Kriging.cpp:2168-2172; KrigingImpl.cpp:611-617), which
+ * lkgpu_predict and LKGPU_EXPORT_Z then use.  beta: [p] (in the model's normalised output scale), or NULL to go back
+ * to the estimated beta. */
+int lkgpu_set_fixed_beta(void* handle, const double* beta);
+
 /* The reference's objective functions, value and analytic gradient in the reference's parametrisation:
  * Kriging::_logLikelihood / _leaveOneOut / _logMargPost (src/lib/Kriging.cpp:214, 353, 488); same calling
  * convention as the Julia shim's lk_kriging_log_likelihood_fun
@@ -138,7 +147,7 @@ int lkgpu_export(void* handle, int which, double* dst);
 /* predict mean / variance factor at m new points (src/lib/KrigingImpl.cpp:145-243),
  * using the model of the last evaluation.  Xn: m*d column-major (normalised),
  * Fn: m*p; beta: [p]; r_on_factor: alpha (nugget) else 1.
- * mean_out[m] = Fn beta + Rstar_on' z ;  var_out[m] = 1 - colsum(Rstar_on^2) + rowsum(Ecirc^2)
+ * mean_out[m] = Fn beta + Rstar_on' z  (z = Estar, or ystar - Fstar beta after lkgpu_set_fixed_beta);  var_out[m] = 1 - colsum(Rstar_on^2) + rowsum(Ecirc^2)
  * (clamped at 0, not yet scaled by sigma2). */
 int lkgpu_predict(void* handle, int m, const double* Xn, const double* Fn, const double* beta, double r_on_factor,
                   double* mean_out, double* var_out);
@@ -165,6 +174,14 @@ int lkgpu_restore_model(void* handle);
  * Schur complement is exhausted.  An evaluation at any other point factors from scratch and drops the kept factor. */
 int lkgpu_append_data(void* handle, int n_u, const double* X_u, const double* y_u, const double* F_u,
                       const double* noise_u);
+/* safe_chol_lower's ladder (src/lib/LinearAlgebra.cpp:68-98) climbs from rung 0 on every call: an evaluation that
+ * is accepted after k diagonal bumps costs k + 1 factorisations.  With the shortcut (default on; flag = 0 or the
+ * environment variable LKGPU_FULL_LADDER=1 restore the plain ladder) an evaluation on a handle whose PREVIOUS
+ * evaluation was accepted on rung k >= 2 enters the ladder at rung k - 1: if that rung is rejected the ladder
+ * continues upwards from there (2 factorisations in the usual case), if it is accepted the whole ladder is run from
+ * rung 0.  Same n_jitter, same factor, same value as the plain ladder whenever acceptance is monotone in the jitter.
+ * stage_ms[LKGPU_CT_RUNGS_SKIPPED] counts the rungs saved. */
+int lkgpu_set_ladder_shortcut(void* handle, int flag);
 /* 1 if the last evaluation on this handle ran as a block extension of a kept factor, else 0 */
 int lkgpu_last_eval_was_update(void* handle);
 

@@ -19,10 +19,10 @@ KERNELS = {"gauss": 0, "exp": 1, "matern3_2": 2, "matern5_2": 3}
 NOISE = {"none": 0, "nugget": 1, "hetero": 2}
 OBJECTIVES = {"LL": 0, "LOO": 1, "LMP": 2}
 EXPORTS = {"L": 0, "R": 1, "Rinv": 2, "Fstar": 3, "Rstar": 4, "ystar": 5, "Estar": 6, "Linv": 7, "x": 8,
-           "loo_err": 9, "loo_s2": 10}
+           "loo_err": 9, "loo_s2": 10, "z": 11}
 N_STAGES = 12
 STAGE_NAMES = ["cov", "chol", "rcond", "solves", "trtri", "lauum", "grad", "extra", "total"]
-COUNTER_NAMES = {"reject_info": 9, "reject_rcond": 10}  # spare stage_ms slots used as counters (include/lkgpu.h)
+COUNTER_NAMES = {"reject_info": 9, "reject_rcond": 10, "rungs_skipped": 11}  # spare stage_ms slots used as counters (include/lkgpu.h)
 
 _dp = C.POINTER(C.c_double)
 
@@ -67,6 +67,8 @@ def lib():
     L.lkgpu_set_data.argtypes = [vp, _dp, _dp, _dp, _dp]
     L.lkgpu_append_data.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp]
     L.lkgpu_set_concurrent.argtypes = [vp, C.c_int]
+    L.lkgpu_set_ladder_shortcut.argtypes = [vp, C.c_int]
+    L.lkgpu_set_fixed_beta.argtypes = [vp, _dp]
     L.lkgpu_commit_model.argtypes = [vp]
     L.lkgpu_restore_model.argtypes = [vp]
     L.lkgpu_last_eval_was_update.argtypes = [vp]
@@ -167,6 +169,17 @@ class Engine:
         """This handle is one of several evaluating at the same time on its device (lkgpu_set_concurrent)."""
         _check(lib().lkgpu_set_concurrent(self._h, int(bool(flag))))
 
+    def set_ladder_shortcut(self, flag=True):
+        """lkgpu_set_ladder_shortcut: enter safe_chol_lower's ladder one rung below the previously accepted one."""
+        _check(lib().lkgpu_set_ladder_shortcut(self._h, int(bool(flag))))
+
+    def set_fixed_beta(self, beta=None):
+        """lkgpu_set_fixed_beta: trend coefficients fixed by the caller (None: estimated)."""
+        b = None if beta is None else np.ascontiguousarray(beta, dtype=np.float64).ravel()
+        if b is not None and b.size != self.p:
+            raise LkgpuError("set_fixed_beta: beta must have p entries")
+        _check(lib().lkgpu_set_fixed_beta(self._h, _ptr(b)))
+
     def commit_model(self):
         """Snapshot the model of the last evaluation as the committed model (m_T, m_M, m_z, ... of the reference)."""
         _check(lib().lkgpu_commit_model(self._h))
@@ -223,7 +236,7 @@ class Engine:
     def export(self, which):
         n, p = self.n, self.p
         shape = {"L": (n, n), "R": (n, n), "Rinv": (n, n), "Linv": (n, n), "Fstar": (n, p), "Rstar": (p, p),
-                 "ystar": (n,), "Estar": (n,), "x": (n,), "loo_err": (n,), "loo_s2": (n,)}[which]
+                 "ystar": (n,), "Estar": (n,), "x": (n,), "loo_err": (n,), "loo_s2": (n,), "z": (n,)}[which]
         buf = np.empty(shape, dtype=np.float64, order="F")
         _check(lib().lkgpu_export(self._h, EXPORTS[which], _ptr(buf)))
         return buf

@@ -38,15 +38,10 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None) ->
     lib_out = os.path.abspath(out) if out else LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           # Global loads bypass the per-SM caches: default loads as ld.global.cg (-dlcm=cg) and no ld.global.nc
-           # (which `const T* __restrict__` kernel parameters would turn into; -D__restrict__= drops the
-           # qualifier).  Defensive, from the hunt for the deviations of overlapping evaluations ("The ring
-           # release, and concurrent handles"); every such buffer is streamed once per kernel, so L1 gives nothing here.
-           "-Xptxas", "-dlcm=cg", "-D__restrict__=",
            "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
            "-o", lib_out] + [os.path.join(CSRC, s) for s in SOURCES]
-    # experiments (tools/validate_relax.sh): LKGPU_BUILD_FLAGS adds flags, LKGPU_BUILD_DROP removes defaults, e.g.
-    #   LKGPU_BUILD_FLAGS="-DLKGPU_NO_WRITER_FENCE" LKGPU_BUILD_DROP="-dlcm=cg -D__restrict__=" python -m libkriging_b200.build --force
+    # experiments: LKGPU_BUILD_FLAGS adds flags, LKGPU_BUILD_DROP removes defaults, LKGPU_BUILD_OUT names the output, e.g.
+    #   LKGPU_BUILD_FLAGS="-DLKGPU_RING_RELEASE=0" LKGPU_BUILD_OUT=libkriging_b200/_variants/lib_A.so python -m libkriging_b200.build
     for drop in os.environ.get("LKGPU_BUILD_DROP", "").split():
         while drop in cmd:
             i = cmd.index(drop)

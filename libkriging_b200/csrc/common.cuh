@@ -28,17 +28,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// Writer-side fence for global data that a LATER kernel reads through TMA (async proxy): make this thread's generic-
-// proxy stores visible at gpu scope and order them before async-proxy accesses.  Defensive: it was introduced while
-// hunting the deviations of overlapping evaluations, whose cause turned out to be the ring-slot release (gemm_dmma.cuh);
-// kept until its removal has been validated on the device ("The ring release, and concurrent handles").
-__device__ __forceinline__ void fence_writes_for_tma() {
-#ifndef LKGPU_NO_WRITER_FENCE  // LKGPU_BUILD_FLAGS=-DLKGPU_NO_WRITER_FENCE python -m libkriging_b200.build --force
-  __threadfence();
-  fence_proxy_async();
-#endif
-}
-
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -151,7 +151,6 @@ cov_build_kernel(const double* __restrict__ X, int n, int d, const __grid_consta
       *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
     }
   }
-  fence_writes_for_tma();  // A is a TMA operand of the factorisation's GEMMs
 }
 
 // ---------------------------------------------------------------------------

@@ -33,8 +33,7 @@ using namespace lk;
 namespace {
 
 thread_local std::string g_last_error;
-// Per-device gate (see Engine::SweepGate): by default the evaluations of different handles never overlap on a
-// device; handles flagged by lkgpu_set_concurrent overlap with each other.
+// Per-device gate (see Engine::SweepGate): mid-size handles overlap, large unflagged ones take the device in turn.
 struct DeviceGate {
   std::mutex m;
   std::condition_variable cv;
@@ -90,11 +89,8 @@ CUtensorMap make_map(double* base, long long rows, long long cols, long long ld,
 }
 
 // The tensor maps of one matrix live in DEVICE memory, one allocation per matrix that is written once and never
-// modified; kernels receive pointers to them.  (They used to be passed by value as __grid_constant__ kernel
-// parameters.  With 8 handles launching the same kernels concurrently, TMA loads then occasionally fetched a tile
-// of ANOTHER handle's matrix -- same coordinates, other buffer: relative errors of 1e-6..1e-3 in single tiles, about
-// one evaluation in 300 -- consistent with a descriptor cached by parameter-space address outliving its launch.
-// A descriptor at an address of its own cannot alias.)
+// modified; kernels receive pointers to them (two 8-byte kernel parameters instead of two 128-byte __grid_constant__
+// descriptors, and the same descriptors serve every launch of the handle).
 struct MatMaps {
   const CUtensorMap* mm = nullptr;  // M-major operand tiles: box {16 rows, 16 k-columns}
   const CUtensorMap* km = nullptr;  // K-major operand tiles: box {16 k-rows, 64 columns}
@@ -164,19 +160,15 @@ __global__ void pad_copy_kernel(const double* __restrict__ src, long long lds, i
   dst[(long long)c * ldd + r] = (r < n) ? src[(long long)c * lds + r] : 0.0;
 }
 
-// Device-side fills and copies in the evaluation path are kernels, not cudaMemsetAsync / cudaMemcpyAsync: with
-// several handles running concurrently on one GPU, copy-engine writes were observed to become visible to the next
-// kernel of the same stream late (stale right-hand sides in ~1 % of the sweeps); stores from a kernel followed by a
-// gpu-scope fence were not.
+// Device-side fills and copies in the evaluation path are small kernels on the handle's own stream (they stay in
+// stream order with the compute kernels and are counted in lkgpu_launch_count).
 __global__ void zero_ints_kernel(int* p, int count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) p[i] = 0;
-  __threadfence();
 }
 __global__ void fill_zero_kernel(double* __restrict__ p, long long count) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     p[i] = 0.0;
-  fence_writes_for_tma();
 }
 __global__ void copy_diag_blocks_kernel(double* __restrict__ dst, long long dst_ld, long long dst_blk,
                                        const double* __restrict__ src, long long src_ld, long long src_blk) {
@@ -186,12 +178,10 @@ __global__ void copy_diag_blocks_kernel(double* __restrict__ dst, long long dst_
     const int c = e / BLK, r = e % BLK;
     d_[c * dst_ld + r] = s_[c * src_ld + r];
   }
-  fence_writes_for_tma();
 }
 __global__ void copy_kernel(double* __restrict__ dst, const double* __restrict__ src, long long count) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i];
-  fence_writes_for_tma();
 }
 
 // dscal slot map (device scalars copied back at the end of an evaluation)
@@ -208,15 +198,14 @@ struct Engine {
   bool debug_simple = false;
   bool use_lookahead = true;
   bool use_step_trsv = false;
-  // Host-side switches for validating the removal of the defensive measures one at a time (tools/validate_relax.sh):
-  bool overlap_default = false;   // LKGPU_OVERLAP_DEFAULT=1: unflagged handles overlap too (no exclusive queue)
-  bool trtri_nosync = false;      // LKGPU_TRTRI_NOSYNC=1: no host wait between TRTRI's launches for overlapping evaluations
-  bool wave_when_shared = false;  // LKGPU_WAVE_WHEN_SHARED=1: overlapping evaluations use the wavefront sweeps
+  // Evaluations of handles with n <= overlap_max_n overlap on the device by default (a mid-size factorisation cannot
+  // fill 148 SMs); larger ones queue unless flagged by lkgpu_set_concurrent.  LKGPU_OVERLAP_MAX_N overrides (0: never).
+  int overlap_max_n = 8192;
   int persistent_update_reserve = 0;
   bool l2_order = true;  // LKGPU_NO_L2_ORDER=1: tile tables sorted by k-length only (the r01c order)
-  bool wave_always = false;
   int wave_grid_cap = 0;  // LKGPU_WAVE_GRID=k: at most k CTAs per sweep (fault localisation)
   bool no_persistent = false;  // LKGPU_NO_PERSISTENT=1: one CTA per tile everywhere (fault localisation)
+  bool ladder_shortcut = true;  // lkgpu_set_ladder_shortcut / LKGPU_FULL_LADDER=1 (see Engine::eval)
   bool use_abort = true;  // LKGPU_NO_ABORT=1: failed Cholesky attempts run to the end (fault localisation)
   int outer_panels = 0;  // Cholesky outer block = outer_panels * 128 columns; 0 = by size (LKGPU_OUTER_PANELS overrides)
   // numerics (LinearAlgebra statics of the reference)
@@ -227,6 +216,10 @@ struct Engine {
   bool est_sigma2 = true, est_nugget = true;
   double sigma2 = 1.0, nugget = 0.0, alpha0 = 1.0;
   std::vector<double> xmin, xmax;
+  // m_est_beta == false: the trend coefficients the caller fixed (lkgpu_set_fixed_beta); they only enter the
+  // committed z = ystar - Fstar beta used by predict (Kriging.cpp:2168-2172), never the objective (KrigingImpl.cpp:113-123)
+  bool has_fixed_beta = false;
+  std::vector<double> fixed_beta;
 
   double *dX = nullptr, *dy = nullptr, *dF = nullptr, *dnoise = nullptr;
   double *A = nullptr, *W = nullptr, *V = nullptr;
@@ -369,15 +362,13 @@ struct Engine {
     if (const char* op = getenv("LKGPU_OUTER_PANELS")) outer_panels = std::max(1, std::min(16, atoi(op)));
     if (const char* wg = getenv("LKGPU_WAVE_GRID")) wave_grid_cap = atoi(wg);
     if (const char* v = getenv("LKGPU_PERSISTENT_UPDATE")) persistent_update_reserve = std::max(0, atoi(v));
-    if (const char* v = getenv("LKGPU_OVERLAP_DEFAULT")) overlap_default = v[0] == '1';
-    if (const char* v = getenv("LKGPU_TRTRI_NOSYNC")) trtri_nosync = v[0] == '1';
-    if (const char* v = getenv("LKGPU_WAVE_WHEN_SHARED")) wave_when_shared = v[0] == '1';
+    if (const char* v = getenv("LKGPU_OVERLAP_MAX_N")) overlap_max_n = std::max(0, atoi(v));
     if (const char* nlo = getenv("LKGPU_NO_L2_ORDER")) l2_order = !(nlo[0] == '1');
-    if (const char* wa = getenv("LKGPU_WAVE_ALWAYS")) wave_always = wa[0] == '1';
     const char* npe = getenv("LKGPU_NO_PERSISTENT");
     no_persistent = npe && npe[0] == '1';
     const char* nab = getenv("LKGPU_NO_ABORT");
     use_abort = !(nab && nab[0] == '1');
+    if (const char* fl = getenv("LKGPU_FULL_LADDER")) ladder_shortcut = !(fl[0] == '1');
     const char* stv = getenv("LKGPU_STEP_TRSV");
     use_step_trsv = stv && stv[0] == '1';
 
@@ -969,11 +960,7 @@ struct Engine {
       a.epilogue = EPI_SETNEG;
       a.table = trtri_tables + lv.off2;
       a.ntiles = (int)lv.n2;
-      // Overlapping evaluations: the host waits for each level's first product before launching the second (a
-      // measure from before the ring-release fix, see SweepGate; 16 waits of ~10 us per evaluation).
-      if (sync_trtri) CUDA_CHECK(cudaStreamSynchronize(s_main));
       gemm(1, mapW, W, mapV, V, a, s_main, true);
-      if (sync_trtri) CUDA_CHECK(cudaStreamSynchronize(s_main));
     }
     have_W = true;
   }
@@ -1015,25 +1002,22 @@ struct Engine {
       CUDA_CHECK(cudaGetLastError());
     }
   }
-  // ---- triangular sweeps (a5): one persistent wavefront kernel per sweep (trsv_wave.cuh) ----
-  // Evaluations of different handles on one device.  History ("The ring release, and concurrent handles"):
-  // with the grids of several handles resident together 2-3 % of the evaluations used to deviate; the cause was the
-  // ring-slot release being scheduled ahead of the stage's last DMMAs (gemm_dmma.cuh / trsv_wave.cuh, fixed: 0
-  // deviations in 2400 overlapping evaluations since).  The conservative policy adopted during the hunt is kept until
-  // its removal has been validated:
-  //  * default: evaluations are EXCLUSIVE per device -- handles queue at this gate, their host work still overlaps --
-  //    and use the wavefront sweeps;
-  //  * handles flagged by lkgpu_set_concurrent overlap with each other (launch-chain sweeps, host-separated TRTRI
-  //    launches): the throughput mode for many mid-size factorisations.
-  bool chain_mode = false;
-  bool sync_trtri = false;
+  // ---- evaluations of different handles on one device ----
+  // A factorisation of n <= ~8192 cannot fill 148 SMs (its panel chain is latency-bound), so the evaluations of
+  // several such handles -- multistart rows (BASELINE cfg 5), NestedKriging sub-models -- overlap: every handle has
+  // its own workspaces and streams and is driven by its own host thread.  Overlapping evaluations return the bits of
+  // a lone handle (every kernel is deterministic and touches only its handle's buffers; validated on the device with
+  // tools/diag_concurrent2.py and tools/diag_foreign.py, profiles/r02_relax_validation.md).  Policy of this gate:
+  //  * handles with n <= overlap_max_n, or flagged by lkgpu_set_concurrent: shared -- they overlap with each other;
+  //  * larger unflagged handles: exclusive -- each fills the GPU by itself, so they queue (their host work still
+  //    overlaps) instead of thrashing each other's L2 working sets.
   bool concurrent_flag = false;  // lkgpu_set_concurrent
   int gate_depth = 0;  // the gate is re-entrant per handle (append -> restore)
   struct SweepGate {
     Engine& e;
     bool shared;
     bool outer;
-    explicit SweepGate(Engine& e_) : e(e_), shared(e_.concurrent_flag || e_.overlap_default), outer(e_.gate_depth++ == 0) {
+    explicit SweepGate(Engine& e_) : e(e_), shared(e_.concurrent_flag || e_.n <= e_.overlap_max_n), outer(e_.gate_depth++ == 0) {
       if (!outer) return;
       DeviceGate& g = g_gate[e.device & 63];
       std::unique_lock<std::mutex> lk(g.m);
@@ -1046,8 +1030,6 @@ struct Engine {
         --g.exclusive_waiting;
         g.exclusive_active = true;
       }
-      e.chain_mode = shared && !e.wave_always && !e.wave_when_shared;
-      e.sync_trtri = shared && !e.trtri_nosync;
     }
     ~SweepGate() {
       --e.gate_depth;
@@ -1061,7 +1043,7 @@ struct Engine {
       g.cv.notify_all();
     }
   };
-  bool sweeps_by_launch_chain() const { return use_step_trsv || chain_mode; }
+  bool sweeps_by_launch_chain() const { return use_step_trsv; }
   void solve_fwd(double* B, int nrhs) {
     if (sweeps_by_launch_chain()) return solve_fwd_steps(B, nrhs);
     solve_wave<false>(B, nrhs);
@@ -1283,6 +1265,7 @@ struct Engine {
     double rc2 = 0.0;
     float ms_cov = 0, ms_chol = 0, ms_rcond = 0, ms_trtri = 0;
     int n_attempt_info = 0, n_attempt_rcond = 0;  // rejected rungs: failed factorisation / rcond below min_rcond
+    int n_rungs_skipped = 0;                      // rungs the ladder shortcut did not have to factor
     // ---- populate_Model's update_eligible (Kriging.cpp:170-188): same theta / extra as the kept factor and more
     //      rows than it has -> block extension; anything else (or an exhausted ladder there) -> from scratch ----
     bool updated = false;
@@ -1296,8 +1279,20 @@ struct Engine {
       keep_n = 0;  // the kept factor is consumed (or overwritten) by this evaluation
     }
     // ---- safe_chol_lower (LinearAlgebra.cpp:43-98): jitter ladder driven from the host ----
-    while (!updated) {
+    // Rung r = r cumulative bumps on the diagonal: diag_add(r) = sum_{i<r} num_nugget 10^i, summed in the ladder's
+    // own order so that a rung reached directly carries bit for bit the jitter it has when climbed to.
+    auto ladder_diag = [&](int r) {
+      double s_ = 0.0;
+      for (int i = 0; i < r; ++i) s_ += num_nugget * std::pow(10.0, i);
+      return s_;
+    };
+    // One attempt: R + diag_add(r) I -> L; accepted iff the factorisation succeeds and rcond_1(L)^2 >= min_rcond.
+    // exact_first: gradient path on the first rung of a handle that has not been climbing -- L^-1 is needed anyway
+    // and its exact 1-norm is a lower bound of what dtrcon estimates, so accepting on it is exactly the reference's
+    // decision; otherwise (or when the exact value says "reject") the estimator decides, as in the reference.
+    auto attempt = [&](int r, bool exact_first) -> bool {
       have_W = false;
+      diag_add = ladder_diag(r);
       CUDA_CHECK(cudaEventRecord(ev_t[1], s_main));
       cov_build(A, alpha, inv_sigma2, diag_add, s_main);
       CUDA_CHECK(cudaEventRecord(ev_t[2], s_main));
@@ -1320,12 +1315,7 @@ struct Engine {
       bool wrong_rcond = rcond_check;
       if (ok && rcond_check) {
         double rc = -1.0;
-        if (need_inverse && inc == 0 && last_n_jitter == 0) {
-          // first rung, gradient path: L^-1 is needed anyway, and its exact 1-norm is a lower bound of what dtrcon
-          // estimates, so accepting on it is exactly the reference's decision; otherwise the estimator decides.
-          // (When the previous evaluation on this handle climbed the ladder, the optimiser is in the numerically
-          // singular region and this rung is likely to be rejected: the O(n^2) estimator goes first and L^-1 is
-          // formed once, after the ladder -- same decisions, one TRTRI less per evaluation.)
+        if (exact_first) {
           CUDA_CHECK(cudaEventRecord(ev_t[3], s_main));
           trtri();
           CUDA_CHECK(cudaEventRecord(ev_t[4], s_main));
@@ -1350,16 +1340,51 @@ struct Engine {
       }
       if (!ok || wrong_rcond) {
         if (!ok) ++n_attempt_info; else ++n_attempt_rcond;
-        if (inc > max_inc)
-          throw LkError{"[ERROR] Exceed max numerical nugget (" + std::to_string(inc) + " x 1e" +
-                        std::to_string(std::log10(num_nugget)) + ") added to force chol matrix"};
-        if (num_nugget <= 0.0)
-          throw LkError{"[ERROR] Cannot add numerical nugget which is not strictly positive: " + std::to_string(num_nugget)};
-        diag_add += num_nugget * std::pow(10.0, inc);
-        ++inc;
-        continue;
+        return false;
       }
-      break;
+      return true;
+    };
+    // what the reference does after a rejected rung r (LinearAlgebra.cpp:75-90)
+    auto after_reject = [&](int r) {
+      if (r > max_inc)
+        throw LkError{"[ERROR] Exceed max numerical nugget (" + std::to_string(r) + " x 1e" +
+                      std::to_string(std::log10(num_nugget)) + ") added to force chol matrix"};
+      if (num_nugget <= 0.0)
+        throw LkError{"[ERROR] Cannot add numerical nugget which is not strictly positive: " + std::to_string(num_nugget)};
+    };
+    if (!updated) {
+      // Ladder shortcut (lkgpu_set_ladder_shortcut, on by default; LKGPU_FULL_LADDER=1 turns it off).  When the
+      // previous evaluation on this handle was accepted on rung k >= 2 -- the optimiser is walking through the
+      // numerically singular region and every evaluation would climb k + 1 rungs = k + 1 full factorisations -- the
+      // ladder is entered at rung k - 1: rejected there (the expected case) it continues upwards as usual, 2
+      // factorisations instead of k + 1, under the one assumption that acceptance is monotone in the jitter (a rung
+      // below a rejected one is rejected).  If rung k - 1 is accepted instead, the assumption says nothing about the
+      // rungs below: the whole ladder is run from rung 0, exactly as without the shortcut.
+      const int hint = ladder_shortcut ? last_n_jitter : 0;
+      int r = 0;
+      bool accepted = false;
+      if (hint >= 2) {
+        if (!attempt(hint - 1, false)) {
+          after_reject(hint - 1);
+          n_rungs_skipped = hint - 1;
+          r = hint;
+        } else {
+          for (r = 0; r < hint - 1 && !accepted; ++r) {
+            accepted = attempt(r, false);
+            if (!accepted) after_reject(r);
+          }
+          if (accepted) --r;                       // the loop's ++r ran once more
+          else accepted = attempt(r = hint - 1, false);  // deterministic: accepted again, and A holds this factor
+        }
+      }
+      while (!accepted) {
+        accepted = attempt(r, need_inverse && r == 0 && last_n_jitter == 0);
+        if (!accepted) {
+          after_reject(r);
+          ++r;
+        }
+      }
+      inc = r;
     }
     if (need_inverse && !have_W) {
       // accepted on a later rung: L^-1 is formed once, after the ladder
@@ -1381,6 +1406,7 @@ struct Engine {
     out->stage_ms[LKGPU_ST_TRTRI] = ms_trtri;
     out->stage_ms[LKGPU_CT_REJECT_INFO] = n_attempt_info;
     out->stage_ms[LKGPU_CT_REJECT_RCOND] = n_attempt_rcond;
+    out->stage_ms[LKGPU_CT_RUNGS_SKIPPED] = n_rungs_skipped;
 
     // ---- sum log diag L ----
     launches += 1;
@@ -1533,6 +1559,18 @@ struct Engine {
         break;
       case LKGPU_EXPORT_X:
         CUDA_CHECK(cudaMemcpy(dst, Xv, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        break;
+      case LKGPU_EXPORT_Z:
+        // m_z (Kriging.cpp:2168-2172): Estar when beta is estimated, ystar - Fstar beta when it is fixed
+        if (!has_fixed_beta) {
+          CUDA_CHECK(cudaMemcpy(dst, Ev, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        } else {
+          std::vector<double> fs((size_t)n * p);
+          CUDA_CHECK(cudaMemcpy2D(fs.data(), (size_t)n * 8, Bv, (size_t)N * 8, (size_t)n * 8, p, cudaMemcpyDeviceToHost));
+          CUDA_CHECK(cudaMemcpy(dst, Bv + (long long)N * p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+          for (int q = 0; q < p; ++q)
+            for (int i = 0; i < n; ++i) dst[i] -= fs[(size_t)q * n + i] * fixed_beta[q];
+        }
         break;
       case LKGPU_EXPORT_LOO_ERR:
       case LKGPU_EXPORT_LOO_S2:
@@ -1745,6 +1783,23 @@ int lkgpu_set_concurrent(void* handle, int flag) {
   LK_TRY
   if (!handle) throw LkError{"null handle"};
   static_cast<Engine*>(handle)->concurrent_flag = flag != 0;
+  LK_CATCH
+}
+
+int lkgpu_set_fixed_beta(void* handle, const double* beta) {
+  LK_TRY
+  if (!handle) throw LkError{"null handle"};
+  Engine* e = static_cast<Engine*>(handle);
+  e->has_fixed_beta = beta != nullptr;
+  if (beta) e->fixed_beta.assign(beta, beta + e->p);
+  else e->fixed_beta.clear();
+  LK_CATCH
+}
+
+int lkgpu_set_ladder_shortcut(void* handle, int flag) {
+  LK_TRY
+  if (!handle) throw LkError{"null handle"};
+  static_cast<Engine*>(handle)->ladder_shortcut = flag != 0;
   LK_CATCH
 }
 

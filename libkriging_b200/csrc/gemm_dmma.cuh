@@ -358,7 +358,6 @@ gemm_dmma_kernel(const CUtensorMap* tmapM, const CUtensorMap* tmapN, const GemmA
         }
       }
     }
-    fence_writes_for_tma();  // C is an operand of later TMA-fed kernels (see common.cuh)
   }
 }
 

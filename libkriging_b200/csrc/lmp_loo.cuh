@@ -112,7 +112,6 @@ scaled_bm_kernel(const double* __restrict__ V, long long ld, const double* __res
       for (int q = 0; q < p; ++q) v -= U[(long long)q * ldu + i] * U[(long long)q * ldu + j];
     Q[(long long)j * ld + i] = sc * v;
   }
-  fence_writes_for_tma();  // Q is a TMA operand of the LOO-gradient product
 }
 
 // out = Vsym * w - U (U^T w) for a lower-block-triangle-stored symmetric V: one warp per row pair sweep.
@@ -167,13 +166,14 @@ cov_rect_kernel(const double* __restrict__ X, int n, int d, const double* __rest
 }
 
 // per new point j: out[j][0] = sum_r S[r,j]^2 ; out[j][1] = sum_r S[r,j] z[r] ; out[j][2+q] = sum_r S[r,j] Fstar[r,q]
+// for q < p, and out[j][2+p] = sum_r S[r,j] ystar[r]  (ystar = column p of [Fstar | ystar]; used when beta is fixed)
 __global__ void __launch_bounds__(256)
 predict_dots_kernel(const double* __restrict__ S, long long lds, const double* __restrict__ z,
                     const double* __restrict__ Fstar, long long ldf, int p, int n, double* __restrict__ out) {
   __shared__ double sh[8];
   const int j = blockIdx.x;
   const double* col = S + (long long)j * lds;
-  for (int q = -2; q < p; ++q) {
+  for (int q = -2; q <= p; ++q) {
     double s = 0.0;
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
       const double a = col[r];
@@ -186,7 +186,7 @@ predict_dots_kernel(const double* __restrict__ S, long long lds, const double* _
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int w = 0; w < 8; ++w) t += sh[w];
-      out[(long long)j * (p + 2) + q + 2] = t;
+      out[(long long)j * (p + 3) + q + 2] = t;
     }
     __syncthreads();
   }
@@ -379,8 +379,8 @@ void Engine::predict(int m, const double* Xn, const double* Fn, const double* be
   const int chunk_max = 1024;
   double* dXn = dalloc<double>((size_t)std::min(m, chunk_max) * d);
   double* dS = dalloc<double>((size_t)N * std::min(m, chunk_max));
-  double* dout = dalloc<double>((size_t)std::min(m, chunk_max) * (p + 2));
-  std::vector<double> hx((size_t)chunk_max * d), ho((size_t)chunk_max * (p + 2));
+  double* dout = dalloc<double>((size_t)std::min(m, chunk_max) * (p + 3));
+  std::vector<double> hx((size_t)chunk_max * d), ho((size_t)chunk_max * (p + 3));
   try {
     for (int j0 = 0; j0 < m; j0 += chunk_max) {
       const int mc = std::min(chunk_max, m - j0);
@@ -403,12 +403,15 @@ void Engine::predict(int m, const double* Xn, const double* Fn, const double* be
       ++launches;
       predict_dots_kernel<<<mc, 256, 0, s_main>>>(dS, N, Ev, Bv, N, p, n, dout);
       CUDA_CHECK(cudaGetLastError());
-      CUDA_CHECK(cudaMemcpyAsync(ho.data(), dout, (size_t)mc * (p + 2) * 8, cudaMemcpyDeviceToHost, s_main));
+      CUDA_CHECK(cudaMemcpyAsync(ho.data(), dout, (size_t)mc * (p + 3) * 8, cudaMemcpyDeviceToHost, s_main));
       CUDA_CHECK(cudaStreamSynchronize(s_main));
       std::vector<double> e(p);
       for (int j = 0; j < mc; ++j) {
-        const double* o = ho.data() + (size_t)j * (p + 2);
-        double mean = o[1];
+        const double* o = ho.data() + (size_t)j * (p + 3);
+        // estimated beta: z = Estar; fixed beta (lkgpu_set_fixed_beta): z = ystar - Fstar beta (Kriging.cpp:2168-2172)
+        double mean = has_fixed_beta ? o[2 + p] : o[1];
+        if (has_fixed_beta)
+          for (int q = 0; q < p; ++q) mean -= o[2 + q] * fixed_beta[q];
         for (int q = 0; q < p; ++q) mean += Fn[(size_t)q * m + j0 + j] * beta[q];
         mean_out[j0 + j] = mean;
         if (var_out) {

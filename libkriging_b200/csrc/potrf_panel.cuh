@@ -234,7 +234,6 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
     if (i >= j) v = *reinterpret_cast<const double2*>(Xb + potf2_blk(i, j) * 1024 + (c & 31) * 32 + (r2 & 31));
     *reinterpret_cast<double2*>(Wblk + (long long)c * ld + r2) = v;
   }
-  fence_writes_for_tma();  // both blocks are TMA operands of the panel TRSM, TRTRI and the sweeps
 }
 
 }  // namespace lk

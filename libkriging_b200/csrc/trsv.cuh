@@ -124,15 +124,19 @@ tri_colsum_abs_kernel(const double* __restrict__ M, long long ld, int n, double*
   if (lane == 0) colsum[warp] = s;
 }
 
+// NaN-propagating maximum (fmax drops NaN operands: a factor with NaN entries would otherwise report a finite
+// norm and pass the isfinite guards of Engine::eval / factor_update).
+__device__ __forceinline__ double nanmax(double a, double b) { return (a != a || b != b) ? NAN : fmax(a, b); }
 __global__ void __launch_bounds__(256) vec_max_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
   __shared__ double sh[8];
   double m = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, v[i]);
-  m = warp_max(m);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = nanmax(m, v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) m = fmax(m, sh[w]);
+    for (int w = 1; w < 8; ++w) m = nanmax(m, sh[w]);
     *out = m;
   }
 }

@@ -124,6 +124,8 @@ arma::vec Kriging::reparam_deriv(const arma::vec& v, const arma::vec& grad) cons
 
 void Kriging::push_params() {
   check(lkgpu_set_params(m_h, m_est_sigma2, m_sigma2, m_est_nugget, m_nugget, m_alpha));
+  // fixed trend coefficients: the committed z is ystar - M beta (Kriging.cpp:2168-2172)
+  check(lkgpu_set_fixed_beta(m_h, m_est_beta ? nullptr : m_beta.memptr()));
 }
 
 double Kriging::objective(int obj, const arma::vec& gamma, arma::vec* grad) {
@@ -445,7 +447,13 @@ void Kriging::commit(const arma::vec& best_gamma) {
   m_theta = v.head(d);
   const bool has_extra = nm != NoiseModel::None;
   const double extra_param = has_extra ? v[d] : 0.0;
-  const double commit_extra = has_extra ? extra_param : 1.0;
+  double commit_extra = has_extra ? extra_param : 1.0;
+  // the committed model is the one the last fit_ofn(best_gamma) built, and _logLikelihood overrides the optimiser's
+  // extra parameter there when it is fixed (Kriging.cpp:221-234)
+  if (m_objective == "LL") {
+    if (nm == NoiseModel::Heterogeneous && !m_est_sigma2) commit_extra = m_sigma2;
+    else if (nm == NoiseModel::Nugget && !m_est_sigma2 && !m_est_nugget) commit_extra = m_sigma2 / (m_sigma2 + m_nugget);
+  }
   double SSE;
   arma::vec betahat;
   model_scalars(m_theta, commit_extra, &SSE, &betahat);
@@ -694,7 +702,7 @@ arma::mat Kriging::M() {
 arma::vec Kriging::z() {
   need_model();
   arma::vec out(m_X.n_rows);
-  check(lkgpu_export(m_h, LKGPU_EXPORT_ESTAR, out.memptr()));
+  check(lkgpu_export(m_h, LKGPU_EXPORT_Z, out.memptr()));
   return out;
 }
 arma::mat Kriging::circ() {

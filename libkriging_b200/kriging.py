@@ -84,6 +84,9 @@ class GpuBackend:
     def set_concurrent(self, flag=True):
         self.engine.set_concurrent(flag)
 
+    def set_fixed_beta(self, beta):
+        self.engine.set_fixed_beta(beta)
+
     def commit(self):
         """The model of the last evaluation becomes the committed one (Kriging.cpp:2156-2173)."""
         self.engine.commit_model()
@@ -207,7 +210,7 @@ class Kriging:
     def is_fitted(self): return not self.m_is_empty
     def T(self): self._need_model(); return self._backend.export("L")
     def M(self): self._need_model(); return self._backend.export("Fstar")
-    def z(self): self._need_model(); return self._backend.export("Estar")
+    def z(self): self._need_model(); return self._backend.export("z")
     def circ(self): self._need_model(); return self._backend.export("Rstar")
 
     def close(self):
@@ -457,49 +460,53 @@ class Kriging:
                 res.update(success=False, error_message=str(e))
             return res
 
-        my_starts = list(range(multistart)) if comm is None else comm.my_starts(multistart)
-        ncon = self._concurrency(len(my_starts), n)
+        # Starts are drawn from a queue: all of them in order without a communicator; with one, the static share
+        # s mod G == r when there is at most one start per rank, else tickets from the group's store (parallel.py).
+        if comm is None:
+            from .parallel import StaticQueue
+            queue_ = StaticQueue(range(multistart))
+            n_mine = multistart
+        else:
+            queue_ = comm.start_queue(multistart)
+            n_mine = -(-multistart // comm.world)
+        ncon = self._concurrency(n_mine, n)
+        results = {}
+
+        def drain(b):
+            while True:
+                s = queue_.next()
+                if s is None:
+                    return
+                results[s] = optimize_worker(s, b)
+
         if ncon <= 1:
-            results = {s: optimize_worker(s) for s in my_starts}
+            drain(be)
         else:
             # Batched-occupancy path (BASELINE cfg 5, SURVEY.md §8b "several handles per device on separate
             # streams"): a mid-size factorisation cannot fill 148 SMs (its panel chain is latency-bound), so this
             # rank's starts run concurrently, one engine handle (own workspaces, own streams) and one host thread
-            # each, flagged by lkgpu_set_concurrent so that their evaluations overlap.  Each start's trajectory equals
-            # the sequential loop's up to the rounding of the triangular sweeps (launch-chain kernels here; engine.cu,
-            # SweepGate); the argmin below is still taken in start order and the committed model is rebuilt by one
-            # exclusive evaluation.
-            import queue
+            # each.  Every start's trajectory is bit for bit the sequential loop's; the argmin below is still taken in
+            # start order.
             from concurrent.futures import ThreadPoolExecutor
-            pool_be = queue.SimpleQueue()
-            pool_be.put(be)
-            if hasattr(be, "set_concurrent"):
-                be.set_concurrent(True)
             extra_be = []
-            for _ in range(ncon - 1):
-                b = self._backend_factory(self.m_X, self.m_y, self.m_F, self.m_kernel, self.m_noise_model,
-                                          self.m_noise, dev)
-                b.set_params(self.m_est_sigma2, self.m_sigma2, self.m_est_nugget, self.m_nugget, self.m_alpha)
-                if hasattr(b, "set_concurrent"):
-                    b.set_concurrent(True)
-                extra_be.append(b)
-                pool_be.put(b)
-
-            def run_start(s):
-                b = pool_be.get()
-                try:
-                    return optimize_worker(s, b)
-                finally:
-                    pool_be.put(b)
-
             try:
+                for _ in range(ncon - 1):
+                    b = self._backend_factory(self.m_X, self.m_y, self.m_F, self.m_kernel, self.m_noise_model,
+                                              self.m_noise, dev)
+                    b.set_params(self.m_est_sigma2, self.m_sigma2, self.m_est_nugget, self.m_nugget, self.m_alpha)
+                    extra_be.append(b)
                 with ThreadPoolExecutor(max_workers=ncon) as ex:
-                    results = dict(zip(my_starts, ex.map(run_start, my_starts)))
+                    for f in [ex.submit(drain, b) for b in [be] + extra_be]:
+                        f.result()
             finally:
+                # statistics of the extra handles are folded into the main one (bench.py reads them there)
+                st = getattr(be, "stats", None)
                 for b in extra_be:
+                    if st is not None and getattr(b, "stats", None):
+                        for k_, v_ in b.stats.items():
+                            st[k_] += v_
                     b.close()
-                if hasattr(be, "set_concurrent") and not self._concurrent_handle:
-                    be.set_concurrent(False)
+        my_starts = sorted(results)
 
         # ---- argmin over successful starts, strict '<' in start order (Kriging.cpp:2097-2114) ----
         if comm is None:
@@ -516,7 +523,8 @@ class Kriging:
             raise RuntimeError(f"All {multistart} optimization attempts failed")
         self.fit_log = dict(multistart=multistart, best_start=best_idx, objective=min_ofn, n_eval=n_eval_total,
                             theta_lower=theta_lower, theta_upper=theta_upper, theta0=theta0, extra0=extra0,
-                            local_starts=my_starts)
+                            local_starts=my_starts, concurrent_starts=ncon,
+                            n_eval_local=sum(r["n_eval"] for r in results.values()))
 
         # ---- commit (Kriging.cpp:2156-2202).  The model of the best start is rebuilt on this rank's device by
         #      one value-only evaluation at gamma* (bit-reproducible; no n x n matrix crosses NVLink). ----
@@ -525,6 +533,14 @@ class Kriging:
         self.m_est_theta = True
         extra_param = float(v[d]) if gd > d else 0.0
         commit_extra = extra_param if gd > d else 1.0
+        # the model the reference commits is the one its last fit_ofn(best_gamma) built, and _logLikelihood overrides
+        # the optimiser's extra parameter there when it is fixed (Kriging.cpp:221-234): m_sigma2 for Heterogeneous with
+        # sigma2 fixed, sigma2 / (sigma2 + nugget) for Nugget with both fixed
+        if objective == "LL":
+            if nm == "hetero" and not self.m_est_sigma2:
+                commit_extra = self.m_sigma2
+            elif nm == "nugget" and not self.m_est_sigma2 and not self.m_est_nugget:
+                commit_extra = self.m_sigma2 / (self.m_sigma2 + self.m_nugget)
         SSE, betahat = be.model_scalars(self.m_theta, commit_extra)
         be.commit()
         self._commit_extra = commit_extra
@@ -675,16 +691,19 @@ class Kriging:
 
     # ---- helpers ----
     def _concurrency(self, n_starts, n):
-        """Number of engine handles this process runs with OVERLAPPING evaluations for its multistart rows.
-        Explicit only: Kriging(..., concurrent_starts=K) or LKGPU_CONCURRENT_STARTS=K (K = 4 is the measured sweet
-        spot for n <= 8192, where one factorisation leaves most SMs idle), limited by free device memory.  Default 1
-        (conservative, see DESIGN.md "The ring release, and concurrent handles" and lkgpu_set_concurrent)."""
+        """Number of engine handles this process runs with OVERLAPPING evaluations for its multistart rows (the
+        batched-occupancy path of BASELINE cfg 5).  A factorisation of n <= 8192 cannot fill 148 SMs -- its panel
+        chain is latency-bound -- so by default such fits keep several starts in flight, one handle and one host
+        thread each (measured on one B200, n = 5000: 10.2 ms per evaluation alone, 5.1 ms with 4 in flight;
+        n = 2500: 4.2 -> 1.2 ms with 8).  Kriging(..., concurrent_starts=K) or LKGPU_CONCURRENT_STARTS=K override;
+        the count is limited by the starts this rank owns and by free device memory.  Results do not depend on it:
+        overlapping evaluations return the bits of a lone handle, and the argmin is taken in start order."""
         import os
         want = self._concurrent_starts
         if want is None and os.environ.get("LKGPU_CONCURRENT_STARTS"):
             want = int(os.environ["LKGPU_CONCURRENT_STARTS"])
         if want is None:
-            want = 1
+            want = 8 if n <= 3072 else (4 if n <= 8192 else 1)
         want = max(1, min(int(want), n_starts))
         if want > 1 and hasattr(self._backend, "max_handles"):
             want = max(1, min(want, self._backend.max_handles()))
@@ -693,6 +712,9 @@ class Kriging:
     def _push_params(self):
         self._backend.set_params(self.m_est_sigma2, self.m_sigma2, getattr(self, "m_est_nugget", True), self.m_nugget,
                                  self.m_alpha)
+        # fixed trend coefficients: the committed z is ystar - M beta (Kriging.cpp:2168-2172)
+        if hasattr(self._backend, "set_fixed_beta"):
+            self._backend.set_fixed_beta(None if self.m_est_beta else self.m_beta)
 
     def _need_model(self):
         if self.m_is_empty or self._backend is None:

@@ -548,7 +548,9 @@ def sigma2_variogram(X, y):
     return 0.5 * float(np.mean(dy2[dX2 >= med]))
 
 
-def predict(pb: Problem, theta, sigma2, Xn, Fn, m: KModel | None = None):
+def predict(pb: Problem, theta, sigma2, Xn, Fn, m: KModel | None = None, fixed_beta=None):
+    """KrigingImpl::predict_impl (KrigingImpl.cpp:145-243).  fixed_beta: the caller's trend coefficients when
+    m_est_beta is false -- then m_z = ystar - M beta (Kriging.cpp:2168-2172) instead of Estar."""
     if m is None:
         m = populate_model(pb, theta)
     dx = pb.X[:, None, :] - Xn[None, :, :]
@@ -558,8 +560,12 @@ def predict(pb: Problem, theta, sigma2, Xn, Fn, m: KModel | None = None):
     # coincident points: exactly 1, no R_on_factor (KrigingImpl.cpp:199-202, dij.is_zero(eps))
     R_on = np.where(np.all(np.abs(dx) <= np.finfo(float).eps, axis=-1), 1.0, R_on)
     Rstar_on = solve_lower(m.L, R_on)
-    z = m.Estar
-    mean = Fn @ m.betahat + Rstar_on.T @ z
+    if fixed_beta is None:
+        z, beta = m.Estar, m.betahat
+    else:
+        beta = np.asarray(fixed_beta, float).ravel()
+        z = m.ystar - m.Fstar @ beta
+    mean = Fn @ beta + Rstar_on.T @ z
     Ecirc = lapack.dtrtrs(m.Rstar, (Fn - Rstar_on.T @ m.Fstar).T, lower=0, trans=1)[0].T
     var = 1.0 - np.sum(Rstar_on * Rstar_on, axis=0) + np.sum(Ecirc * Ecirc, axis=1)
     var = np.maximum(var, 0.0)

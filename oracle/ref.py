@@ -23,7 +23,7 @@ def available() -> bool:
 def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL", regmodel="constant",
         normalize=False, mode="eval", optim="none", theta=None, gamma=None, grad=True, reps=1,
         sigma2=None, est_sigma2=None, nugget=None, est_nugget=None, Xn=None, threads=None,
-        loovec=False, dump=False, extra_cfg=None, timeout=None, update=None):
+        loovec=False, dump=False, extra_cfg=None, timeout=None, update=None, beta=None):
     """Run the reference on (X, y).  theta: (nt, d) start / evaluation point(s);
     gamma: evaluation point incl. the extra parameter (alpha | sigma2)."""
     if not available():
@@ -49,6 +49,10 @@ def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL",
             cfg["sigma2"] = repr(float(sigma2)); cfg["est_sigma2"] = int(bool(est_sigma2))
         if nugget is not None:
             cfg["nugget"] = repr(float(nugget)); cfg["est_nugget"] = int(bool(est_nugget))
+        if beta is not None:  # fixed trend coefficients (is_beta_estim = false)
+            b = np.ascontiguousarray(beta, dtype=np.float64).ravel()
+            cfg["beta_n"] = b.size
+            b.tofile(os.path.join(wd, "beta.bin"))
         if Xn is not None:
             Xn = np.asfortranarray(Xn, dtype=np.float64)
             cfg["m"] = Xn.shape[0]

@@ -104,6 +104,12 @@ int main(int argc, char** argv) {
   if (exists(wd + "/theta.bin")) prm.theta = arma::mat(read_bin(wd + "/theta.bin", (size_t)nt * d).data(), nt, d);
   if (cfg.count("sigma2")) { prm.sigma2 = getd("sigma2", 1.0); prm.is_sigma2_estim = geti("est_sigma2", 0) != 0; }
   if (cfg.count("nugget")) { prm.nugget = getd("nugget", 0.0); prm.is_nugget_estim = geti("est_nugget", 0) != 0; }
+  // fixed trend coefficients (Parameters::beta with is_beta_estim = false): <workdir>/beta.bin, beta_n entries
+  if (geti("beta_n", 0) > 0) {
+    const int bn = geti("beta_n", 0);
+    prm.beta = arma::vec(read_bin(wd + "/beta.bin", bn).data(), bn);
+    prm.is_beta_estim = false;
+  }
   Trend::RegressionModel rm = Trend::fromString(regmodel);
 
   std::ostringstream js;

@@ -6,6 +6,7 @@ host memory and stores value + gradient + the measured wall time in tests/golden
   cfg2   Kriging('matern5_2') LL + gradient, n = 20000, d = 10, theta = 0.5   (BASELINE configs[1]; ~50 GB host RAM)
   cfg3   Kriging('exp') LOO + gradient,     n = 10000, d = 6,  theta = 0.8    (BASELINE configs[2])
   cfg5   Kriging('gauss') LL + gradient,    n = 5000,  d = 20, theta = 1.2    (BASELINE configs[4] shape)
+  big    cfg-2 shape at n = 18000 (what fits this container; cfg2 itself was generated on the GPU box's host, 16 cores)
   mid    several n = 1500..3000 cases (12..24 panels of 128: look-ahead / outer blocks / TRTRI recursion depth > 1)
 
 Inputs are the seeded generator shared with tests/util.py:synth(n, d, seed, 'smooth') and bench.py:synth (same X,
@@ -27,7 +28,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import ref  # noqa: E402
 
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refgen_fullsize.json")
+OUT = os.environ.get("GOLDEN_OUT") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "refgen_fullsize.json")
 
 
 def synth(n, d, seed):
@@ -39,6 +40,8 @@ def synth(n, d, seed):
 
 CASES = {
     "cfg2": dict(n=20000, d=10, seed=123, kernel="matern5_2", noise_model="none", objective="LL", theta=0.5),
+    # the largest cfg-2-shaped case this container's 62 GB hold (the reference peaks at 19.6 x 8 n^2 bytes): 141 panels
+    "big-ll-m52-n18000": dict(n=18000, d=10, seed=123, kernel="matern5_2", noise_model="none", objective="LL", theta=0.5),
     "cfg3": dict(n=10000, d=6, seed=123, kernel="exp", noise_model="none", objective="LOO", theta=0.8),
     "cfg5": dict(n=5000, d=20, seed=123, kernel="gauss", noise_model="none", objective="LL", theta=1.2),
     "mid-ll-m52-n3000": dict(n=3000, d=10, seed=124, kernel="matern5_2", noise_model="none", objective="LL", theta=0.5),

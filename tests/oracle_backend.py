@@ -18,6 +18,9 @@ class OracleBackend:
         pb = self.pb
         pb.est_sigma2, pb.sigma2, pb.est_nugget, pb.nugget, pb.alpha = est_sigma2, sigma2, est_nugget, nugget, alpha
 
+    def set_fixed_beta(self, beta):
+        self.fixed_beta = None if beta is None else np.asarray(beta, float).copy()
+
     def theta_bounds(self, lower_factor, upper_factor, heuristic):
         return ko.theta_bounds(self.pb.X, self.pb.y, lower_factor, upper_factor, heuristic)
 
@@ -64,13 +67,15 @@ class OracleBackend:
 
     def export(self, which):
         m = self.model
-        return {"L": m.L, "Fstar": m.Fstar, "Estar": m.Estar, "Rstar": m.Rstar}[which]
+        fb = getattr(self, "fixed_beta", None)
+        z = m.Estar if fb is None else m.ystar - m.Fstar @ fb
+        return {"L": m.L, "Fstar": m.Fstar, "Estar": m.Estar, "Rstar": m.Rstar, "z": z}[which]
 
     def predict(self, Xn, Fn, beta, r_on_factor):
         pb = self.pb
         saved = pb.alpha
         pb.alpha = r_on_factor
-        mean, sd = ko.predict(pb, self.theta, 1.0, Xn, Fn, self.model)
+        mean, sd = ko.predict(pb, self.theta, 1.0, Xn, Fn, self.model, fixed_beta=getattr(self, "fixed_beta", None))
         pb.alpha = saved
         return mean, sd * sd
 

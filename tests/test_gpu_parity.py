@@ -133,6 +133,40 @@ def test_jitter_ladder_matches_reference_semantics(capi):
         assert r2["n_jitter"] == m2.n_jitter
 
 
+def test_ladder_shortcut_equals_the_full_ladder(capi):
+    """lkgpu_set_ladder_shortcut: a handle whose previous evaluation was accepted on rung k >= 2 enters
+    safe_chol_lower's ladder (LinearAlgebra.cpp:68-98) at rung k - 1.  Along a walk through the numerically singular
+    region (theta up, then down, then a jump back to a well-conditioned point) every evaluation must return the
+    n_jitter, value and gradient of the plain ladder bit for bit, while factoring fewer rungs."""
+    X, y, _ = synth(500, 2, 27)
+    F = np.ones((500, 1))
+    # num_nugget = 1e-15 makes the ladder long at this small n (the oracle climbs 0, 2, 3, 4, 5, 6 rungs along theta
+    # = 0.05 .. 1.1; at n = 20000 the default 1e-10 does the same)
+    walk = [0.05, 0.1, 0.15, 0.2, 0.5, 1.1, 2.0, 1.1, 0.3, 0.12, 2.6, 0.05, 0.2, 1.4]
+    with capi.Engine(X, y, F, kernel="gauss") as fast, capi.Engine(X, y, F, kernel="gauss") as plain:
+        fast.set_numerics(num_nugget=1e-15)
+        plain.set_numerics(num_nugget=1e-15)
+        plain.set_ladder_shortcut(False)
+        pb = ko.Problem(X=X, y=y, F=F, kernel="gauss", num=ko.Numerics(num_nugget=1e-15))
+        skipped, rungs = 0, []
+        for t in walk:
+            th = np.array([t, 0.9 * t])
+            v1, g1, i1 = fast.objective("LL", th, True, with_info=True)
+            v0, g0, i0 = plain.objective("LL", th, True, with_info=True)
+            assert i0["rungs_skipped"] == 0
+            assert i1["n_jitter"] == i0["n_jitter"], (t, i1["n_jitter"], i0["n_jitter"])
+            assert v1 == v0 and np.array_equal(g1, g0), t
+            skipped += i1["rungs_skipped"]
+            rungs.append(i0["n_jitter"])
+            if t in (0.15, 1.1):
+                assert i0["n_jitter"] == ko.populate_model(pb, th).n_jitter  # the reference's count
+        assert max(rungs) >= 5 and skipped >= 10, (rungs, skipped)
+        # value-only evaluations take the same ladder
+        for t in (2.4, 0.4):
+            th = np.array([t, 0.9 * t])
+            assert fast.objective("LL", th, False)[0] == plain.objective("LL", th, False)[0]
+
+
 def test_value_only_path_equals_gradient_path(capi):
     X, y, _ = synth(700, 5, 3)
     F = np.ones((700, 1))

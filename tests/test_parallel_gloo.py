@@ -1,5 +1,6 @@
-"""world_size-2 gloo tests (CPU) of the multistart sharding: rank r runs the starts {s : s mod G == r}, one
-all_gather + one broadcast pick the reference's argmin, and the sharded fit equals the single-process fit."""
+"""world_size-2 gloo tests (CPU) of the multistart sharding: starts are handed out statically (s mod G == r, at most
+one per rank) or by the store-backed queue (more starts than ranks), one all-reduce picks the reference's argmin, and
+the sharded fit equals the single-process fit bit for bit."""
 import os
 import socket
 
@@ -39,8 +40,13 @@ def _worker(rank, world, port, q):
         X, y, _ = synth(50, 2, 5, "smooth")
         k = Kriging("matern5_2", backend_factory=OracleBackend)
         k.fit(y, X, optim="BFGS4", comm=comm)
-        q.put((rank, k.theta().tolist(), k.sigma2(), k.fit_log["best_start"], k.fit_log["local_starts"],
-               k._backend.n_objective_calls))
+        out = [rank, k.theta().tolist(), k.sigma2(), k.fit_log["best_start"], k.fit_log["local_starts"],
+               k.fit_log["n_eval_local"], k.fit_log["n_eval"]]
+        # (c) one start per rank: static assignment s mod G == r
+        k2 = Kriging("matern5_2", backend_factory=OracleBackend)
+        k2.fit(y, X, optim="BFGS2", comm=comm)
+        out += [k2.theta().tolist(), k2.fit_log["local_starts"]]
+        q.put(tuple(out))
     finally:
         dist.destroy_process_group()
 
@@ -61,8 +67,12 @@ def test_sharded_multistart_equals_single_process():
     X, y, _ = synth(50, 2, 5, "smooth")
     k = Kriging("matern5_2", backend_factory=OracleBackend, concurrent_starts=1)
     k.fit(y, X, optim="BFGS4")
-    for rank, theta, s2, best, local, ncalls in out:
+    k2 = Kriging("matern5_2", backend_factory=OracleBackend, concurrent_starts=1)
+    k2.fit(y, X, optim="BFGS2")
+    for rank, theta, s2, best, local, nloc, ntot, theta2, local2 in out:
         assert theta == k.theta().tolist() and s2 == k.sigma2() and best == k.fit_log["best_start"]
-        assert local == [s for s in range(4) if s % 2 == rank]
-    # the work really was split: each rank evaluated fewer objectives than the single process
-    assert all(o[5] < k._backend.n_objective_calls for o in out)
+        assert ntot == k.fit_log["n_eval"]
+        assert theta2 == k2.theta().tolist() and local2 == [rank]
+    # dynamic queue: the four starts were split between the ranks, each run exactly once
+    assert sorted(out[0][4] + out[1][4]) == [0, 1, 2, 3]
+    assert out[0][5] + out[1][5] == k.fit_log["n_eval"]
