@@ -44,6 +44,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before any CUDA context (libkriging_b200/__init__.py)
 
 UNIT = "evals/s"
 
@@ -386,7 +387,7 @@ def fit_block(Kriging, cfg, X, y, optim, local, comm, world, max_over_ranks, bar
     st = dict(getattr(k._backend, "stats", {}) or {})
     fit = {"wall_s": t_fit, "optim": optim, "n_eval_all_ranks": int(k.fit_log["n_eval"]),
            "starts": int(k.fit_log["multistart"]), "best_start": int(k.fit_log["best_start"]),
-           "objective_at_fit": float(k.fit_log["objective"]), "theta": [float(t) for t in k.theta()],
+           "LL_at_fit": -float(k.fit_log["objective"]), "theta": [float(t) for t in k.theta()],
            "sigma2": float(k.sigma2()), "concurrent_starts_per_gpu": int(k.fit_log.get("concurrent_starts", 1)),
            "start_assignment": "static s mod G" if int(k.fit_log["multistart"]) <= world else
                                "dynamic queue (process-group store counter)" if world > 1 else "in order"}
@@ -606,6 +607,29 @@ def run_b200_arm(args, cfg):
                         concurrent=cfg.get("handles"))
         fit["y"] = y_desc
 
+    # ---- the same fit through the C++ host (lkgpu::Kriging: Armadillo API + lbfgsb_cpp loop on the CPU, every
+    #      objective evaluation through the C ABI) -- the host north_star names; single process, this rank's GPU ----
+    fit_cpp = None
+    if fit is not None and rank == 0 and not args.no_cpp_host and cfg["noise_model"] == "none":
+        try:
+            from libkriging_b200.host import driver as cpp
+            if cpp.available():
+                t0 = time.perf_counter()
+                r = cpp.run(X, y_fit, kernel=cfg["kernel"], objective="LL", mode="fit", optim="BFGS", device=local,
+                            timeout=900)
+                fit_cpp = {"host": "libkriging_b200/host/lkgpu_host_driver (C++: Armadillo + lbfgsb_cpp)",
+                           "wall_s": float(r["fit_s"]), "wall_s_incl_process_start": time.perf_counter() - t0,
+                           "n_eval": int(r["n_eval"]), "LL_at_fit": float(r["objective_at_fit"]),
+                           "theta": [float(t) for t in r["theta"]], "sigma2": float(r["sigma2"])}
+                if world == 1:
+                    th_py = np.asarray(fit["theta"])
+                    fit_cpp["theta_relerr_vs_python_host"] = float(np.max(np.abs(np.asarray(r["theta"]) - th_py) / th_py))
+                    fit_cpp["LL_relerr_vs_python_host"] = abs(fit_cpp["LL_at_fit"] - fit["LL_at_fit"]) / abs(fit["LL_at_fit"])
+            else:
+                fit_cpp = {"unavailable": "libkriging_b200/host/_build/lkgpu_host_driver not built"}
+        except Exception as ex:  # pragma: no cover
+            fit_cpp = {"failed": str(ex)[:300]}
+
     # ---- batched-occupancy path (BASELINE configs[4] shape) ----
     batched = None
     if not args.no_batched and (args.config == 2 or cfg.get("handles")):
@@ -717,6 +741,7 @@ def run_b200_arm(args, cfg):
         "cpu_baseline": cpu,
         "parity_vs_reference": parity,
         "fit": fit,
+        "fit_cpp_host": fit_cpp,
         "batched": batched,
         "update": update,
         "stages_ms": stages,
@@ -742,6 +767,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-update", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--no-cpp-host", action="store_true")
     ap.add_argument("--peak", default="cublas", choices=["cublas", "max"])
     ap.add_argument("--ref-budget", type=float, default=1300.0,
                     help="reference arm: seconds allowed for the full-size run (the driver's limit is 1800 s)")

@@ -177,10 +177,10 @@ int lkgpu_append_data(void* handle, int n_u, const double* X_u, const double* y_
 /* safe_chol_lower's ladder (src/lib/LinearAlgebra.cpp:68-98) climbs from rung 0 on every call: an evaluation that
  * is accepted after k diagonal bumps costs k + 1 factorisations.  With the shortcut (default on; flag = 0 or the
  * environment variable LKGPU_FULL_LADDER=1 restore the plain ladder) an evaluation on a handle whose PREVIOUS
- * evaluation was accepted on rung k >= 2 enters the ladder at rung k - 1: if that rung is rejected the ladder
- * continues upwards from there (2 factorisations in the usual case), if it is accepted the whole ladder is run from
- * rung 0.  Same n_jitter, same factor, same value as the plain ladder whenever acceptance is monotone in the jitter.
- * stage_ms[LKGPU_CT_RUNGS_SKIPPED] counts the rungs saved. */
+ * evaluation was accepted on rung k >= 2 enters the ladder at rung k: rejected there it climbs on as usual; accepted
+ * there, the factor is set aside and the rungs below are tried downwards until one is rejected (usually the first:
+ * 2 factorisations instead of k + 1).  Same n_jitter, same factor, same value as the plain ladder whenever
+ * acceptance is monotone in the jitter.  stage_ms[LKGPU_CT_RUNGS_SKIPPED] counts the factorisations saved. */
 int lkgpu_set_ladder_shortcut(void* handle, int flag);
 /* 1 if the last evaluation on this handle ran as a block extension of a kept factor, else 0 */
 int lkgpu_last_eval_was_update(void* handle);

@@ -88,7 +88,15 @@ def lib():
 
 
 def _ptr(a):
-    return a.ctypes.data_as(_dp) if a is not None else None
+    return a.ctypes.data_as(_dp) if a is not None and a.size > 0 else None
+
+
+def _as_trend(F, n):
+    """n x p trend matrix, column-major; p = 0 (regmodel 'none') is an n x 0 array."""
+    F = np.asarray(F, dtype=np.float64)
+    if F.size == 0:
+        return np.zeros((n, 0), order="F")
+    return np.asfortranarray(F.reshape(n, -1))
 
 
 def _check(rc):
@@ -116,7 +124,7 @@ class Engine:
     def __init__(self, X, y, F, *, kernel="gauss", noise_model="none", noise=None, device=0):
         X = np.asfortranarray(X, dtype=np.float64)
         y = np.ascontiguousarray(y, dtype=np.float64).ravel()
-        F = np.asfortranarray(np.asarray(F, dtype=np.float64).reshape(X.shape[0], -1))
+        F = _as_trend(F, X.shape[0])
         self.n, self.d = X.shape
         self.p = F.shape[1]
         self.kernel, self.noise_model, self.device = kernel, noise_model, device
@@ -148,7 +156,7 @@ class Engine:
     def set_data(self, X, y, F, noise=None):
         X = np.asfortranarray(X, dtype=np.float64)
         y = np.ascontiguousarray(y, dtype=np.float64).ravel()
-        F = np.asfortranarray(np.asarray(F, dtype=np.float64).reshape(X.shape[0], -1))
+        F = _as_trend(F, X.shape[0])
         nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64).ravel()
         _check(lib().lkgpu_set_data(self._h, _ptr(X), _ptr(y), _ptr(F), _ptr(nz)))
 
@@ -158,7 +166,7 @@ class Engine:
         X_u = np.asfortranarray(np.asarray(X_u, dtype=np.float64).reshape(-1, self.d))
         n_u = X_u.shape[0]
         y_u = np.ascontiguousarray(y_u, dtype=np.float64).ravel()
-        F_u = np.asfortranarray(np.asarray(F_u, dtype=np.float64).reshape(n_u, -1))
+        F_u = _as_trend(F_u, n_u)
         if y_u.size != n_u or F_u.shape[1] != self.p:
             raise LkgpuError("append_data: y_u / F_u do not match X_u")
         nz = None if noise_u is None else np.ascontiguousarray(noise_u, dtype=np.float64).ravel()
@@ -244,7 +252,7 @@ class Engine:
     def predict(self, Xn, Fn, beta, r_on_factor=1.0, want_var=True):
         Xn = np.asfortranarray(Xn, dtype=np.float64)
         m = Xn.shape[0]
-        Fn = np.asfortranarray(np.asarray(Fn, dtype=np.float64).reshape(m, -1))
+        Fn = _as_trend(Fn, m)
         beta = np.ascontiguousarray(beta, dtype=np.float64).ravel()
         mean = np.empty(m)
         var = np.empty(m) if want_var else None

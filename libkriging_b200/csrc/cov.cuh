@@ -24,11 +24,28 @@ struct KernelParams {
   double inv_theta[LK_MAX_D];
 };
 
-// ln-free correlation factor pieces. u = (x_i - x_j)/theta_k.
+// ln-free correlation factor pieces.  The pair kernels stage X pre-scaled by c_K / theta_k (c = 1, 1, sqrt3, sqrt5),
+// so per pair and dimension they see  u = c_K (x_i - x_j) / theta_k  directly:
 //   gauss:  rho = exp(-0.5 sum u^2)
 //   exp:    rho = exp(-sum |u|)
-//   m32:    rho = prod(1+s) exp(-sum s),            s = sqrt3 |u|   == exp(-sum(s - log1p(s)))
-//   m52:    rho = prod(1+s+s^2/3) exp(-sum s),      s = sqrt5 |u|   == exp(-sum(s - log1p(s+s^2/3)))
+//   m32:    rho = prod(1+s) exp(-sum s),            s = |u| = sqrt3 |dx|/theta   == exp(-sum(s - log1p(s)))
+//   m52:    rho = prod(1+s+s^2/3) exp(-sum s),      s = |u| = sqrt5 |dx|/theta   == exp(-sum(s - log1p(s+s^2/3)))
+// Every per-pair-per-dimension step is a handful of FP64 pipe operations (ncu of round 1's kernels: FP64 pipe 57 %
+// busy, the rest issue slots -- the divisions of 1 + s + s^2/3 and of the log-derivatives were most of both).
+template <int KERNEL>
+__host__ __device__ constexpr double corr_scale() {
+  return KERNEL == 2 ? LK_SQRT3 : (KERNEL == 3 ? LK_SQRT5 : 1.0);
+}
+// 1 / x for x in [1, 1e300): hardware seed (rcp.approx.ftz.f64, ~2^-23) + two Newton steps = full precision to the
+// last ulp or two -- no special-case paths, 5 FP64 operations against the ~30 of an IEEE division.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 template <int KERNEL>
 __device__ __forceinline__ void corr_accum(double u, double& esum, double& prod) {
   if (KERNEL == 0) {
@@ -36,13 +53,13 @@ __device__ __forceinline__ void corr_accum(double u, double& esum, double& prod)
   } else if (KERNEL == 1) {
     esum += fabs(u);
   } else if (KERNEL == 2) {
-    const double s = LK_SQRT3 * fabs(u);
+    const double s = fabs(u);
     esum += s;
     prod *= (1.0 + s);
   } else {
-    const double s = LK_SQRT5 * fabs(u);
+    const double s = fabs(u);
     esum += s;
-    prod *= (1.0 + s + (s * s) / 3.0);
+    prod *= fma(s, fma(s, 1.0 / 3.0, 1.0), 1.0);
   }
 }
 template <int KERNEL>
@@ -51,18 +68,16 @@ __device__ __forceinline__ double corr_finish(double esum, double prod) {
   if (KERNEL == 1) return exp(-esum);
   return prod * exp(-esum);
 }
-// theta_k * dln rho / dtheta_k as a function of u = dx/theta_k  (the 1/theta_k is applied at the end)
+// theta_k * dln rho / dtheta_k as a function of the scaled u  (the 1/theta_k is applied by the host at the end):
+//   gauss u^2 ; exp |u| ; m32 s^2 / (1 + s) ; m52 (1 + s) (s^2/3) / (1 + s + s^2/3) = (1 + s) s^2 / (3 (1 + s) + s^2)
 template <int KERNEL>
 __device__ __forceinline__ double dlnrho_times_theta(double u) {
   if (KERNEL == 0) return u * u;
   if (KERNEL == 1) return fabs(u);
-  if (KERNEL == 2) {
-    const double s = LK_SQRT3 * fabs(u);
-    return (s * s) / (1.0 + s);
-  }
-  const double s = LK_SQRT5 * fabs(u);
-  const double a = 1.0 + s, b = (s * s) / 3.0;
-  return (a * b) / (a + b);
+  const double s = fabs(u);
+  const double a = 1.0 + s, s2 = s * s;
+  if (KERNEL == 2) return s2 * fast_rcp(a);
+  return (a * s2) * fast_rcp(fma(3.0, a, s2));
 }
 
 // lower-triangle tile id -> (ti >= tj)
@@ -74,13 +89,14 @@ __device__ __forceinline__ void tri_tile(int id, int& ti, int& tj) {
   tj = id - t * (t + 1) / 2;
 }
 
-// stage X rows [r0, r0+64) scaled by 1/theta into smem as xs[k*64 + r]
+// stage X rows [r0, r0+64) scaled by c_K / theta into smem as xs[k*64 + r]
+template <int KERNEL>
 __device__ __forceinline__ void stage_x(const double* __restrict__ X, int n, int d, const KernelParams& kp, int r0,
                                         double* xs) {
   for (int e = threadIdx.x; e < d * PT; e += PAIR_THREADS) {
     const int k = e / PT, r = e % PT;
     const int row = r0 + r;
-    xs[e] = (row < n) ? X[(long long)k * n + row] * kp.inv_theta[k] : 0.0;
+    xs[e] = (row < n) ? X[(long long)k * n + row] * (kp.inv_theta[k] * corr_scale<KERNEL>()) : 0.0;
   }
 }
 
@@ -107,8 +123,8 @@ cov_build_kernel(const double* __restrict__ X, int n, int d, const __grid_consta
     ti += shift;
     tj += shift;
     __syncthreads();
-    stage_x(X, n, d, kp, ti * PT, xi);
-    stage_x(X, n, d, kp, tj * PT, xj);
+    stage_x<KERNEL>(X, n, d, kp, ti * PT, xi);
+    stage_x<KERNEL>(X, n, d, kp, tj * PT, xj);
     __syncthreads();
     double es[4][4], pr[4][4];
 #pragma unroll
@@ -183,8 +199,8 @@ grad_reduce_kernel(const double* __restrict__ X, int n, int d, const __grid_cons
     int ti, tj;
     tri_tile(tile, ti, tj);
     __syncthreads();
-    stage_x(X, n, d, kp, ti * PT, xi);
-    stage_x(X, n, d, kp, tj * PT, xj);
+    stage_x<KERNEL>(X, n, d, kp, ti * PT, xi);
+    stage_x<KERNEL>(X, n, d, kp, tj * PT, xj);
     if (threadIdx.x < PT) {
       const int row = ti * PT + threadIdx.x;
       xvi[threadIdx.x] = (row < n) ? avec[row] : 0.0;

@@ -33,6 +33,12 @@ using namespace lk;
 namespace {
 
 thread_local std::string g_last_error;
+
+// Hardware work queues: the default of 8 connections maps the 2 streams x (up to 16) handles that run concurrently
+// on one device onto 8 queues, with false dependencies between streams that share one (measured, 8 handles of
+// n = 5000 in flight: 5.13 ms per evaluation with 8 connections, 4.70 ms with 32).  The variable is read when the CUDA
+// context is created, so it is set when this library is loaded -- unless the user has set it.
+__attribute__((constructor)) void lk_set_max_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 // Per-device gate (see Engine::SweepGate): mid-size handles overlap, large unflagged ones take the device in turn.
 struct DeviceGate {
   std::mutex m;
@@ -235,7 +241,8 @@ struct Engine {
   bool have_loo = false;
   double* logdet_blocks = nullptr;
   int* dinfo = nullptr;       // [0] chol info, [1] gls info
-  int* wave_ctl = nullptr;    // wavefront sweeps: [0] ticket counter, [1 + i] flag of row block i
+  int* wave_ctl = nullptr;    // wavefront sweeps: [0] ticket counter
+  double* wave_z = nullptr;   // wavefront sweeps: published solution blocks, N x WAVE_MAX_RHS (trsv_wave.cuh)
   double* dscal = nullptr;    // small device scalars / results (64 doubles)
   double* dpartial = nullptr; // reduction partials
   size_t partial_doubles = 0;
@@ -289,6 +296,11 @@ struct Engine {
     if (dinfo) cudaFree(dinfo);
     if (wave_ctl) cudaFree(wave_ctl);
     wave_ctl = nullptr;
+    if (wave_z) cudaFree(wave_z);
+    wave_z = nullptr;
+    if (ladder_D) cudaFree(ladder_D);
+    if (ladder_logdet) cudaFree(ladder_logdet);
+    ladder_D = ladder_logdet = nullptr;
     if (trtri_tables) cudaFree(trtri_tables);
     if (lauum_table) cudaFree(lauum_table);
     if (loo_table) cudaFree(loo_table);
@@ -342,7 +354,7 @@ struct Engine {
     kernel = kernel_;
     noise_model = noise_model_;
     if (n < 1 || d < 1 || d > LK_MAX_D) throw LkError{"lkgpu_create: need n >= 1 and 1 <= d <= 64"};
-    if (p < 1 || p > 128) throw LkError{"lkgpu_create: need 1 <= p <= 128 trend columns"};
+    if (p < 0 || p > 128) throw LkError{"lkgpu_create: need 0 <= p <= 128 trend columns"};  // p = 0: regmodel "none"
     if (kernel < 0 || kernel > 3) throw LkError{"lkgpu_create: unknown kernel id"};
     if (noise_model < 0 || noise_model > 2) throw LkError{"lkgpu_create: unknown noise model"};
     if (noise_model == LKGPU_NOISE_HETERO && !noise) throw LkError{"lkgpu_create: heterogeneous noise needs a noise vector"};
@@ -462,6 +474,7 @@ struct Engine {
     mapW = maps_of(W, true);
     mapV = maps_of(V, true);
     wave_ctl = dalloc<int>(nb + 1);
+    wave_z = dalloc<double>((size_t)N * WAVE_MAX_RHS);
     build_plans();
   }
 
@@ -562,8 +575,10 @@ struct Engine {
       // data: column-major with the new column stride n
       CUDA_CHECK(cudaMemcpy2DAsync(dX, (size_t)n * 8, X_old, (size_t)n_old * 8, (size_t)n_old * 8, d, cudaMemcpyDeviceToDevice, s_main));
       CUDA_CHECK(cudaMemcpy2DAsync(dX + n_old, (size_t)n * 8, X_u, (size_t)n_u * 8, (size_t)n_u * 8, d, cudaMemcpyHostToDevice, s_main));
-      CUDA_CHECK(cudaMemcpy2DAsync(dF, (size_t)n * 8, F_old, (size_t)n_old * 8, (size_t)n_old * 8, p, cudaMemcpyDeviceToDevice, s_main));
-      CUDA_CHECK(cudaMemcpy2DAsync(dF + n_old, (size_t)n * 8, F_u, (size_t)n_u * 8, (size_t)n_u * 8, p, cudaMemcpyHostToDevice, s_main));
+      if (p > 0) {
+        CUDA_CHECK(cudaMemcpy2DAsync(dF, (size_t)n * 8, F_old, (size_t)n_old * 8, (size_t)n_old * 8, p, cudaMemcpyDeviceToDevice, s_main));
+        CUDA_CHECK(cudaMemcpy2DAsync(dF + n_old, (size_t)n * 8, F_u, (size_t)n_u * 8, (size_t)n_u * 8, p, cudaMemcpyHostToDevice, s_main));
+      }
       CUDA_CHECK(cudaMemcpyAsync(dy, y_old, (size_t)n_old * 8, cudaMemcpyDeviceToDevice, s_main));
       CUDA_CHECK(cudaMemcpyAsync(dy + n_old, y_u, (size_t)n_u * 8, cudaMemcpyHostToDevice, s_main));
       if (dnoise) {
@@ -605,7 +620,7 @@ struct Engine {
   void set_data(const double* X, const double* y, const double* F, const double* noise) {
     CUDA_CHECK(cudaMemcpyAsync(dX, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, s_main));
     CUDA_CHECK(cudaMemcpyAsync(dy, y, (size_t)n * 8, cudaMemcpyHostToDevice, s_main));
-    CUDA_CHECK(cudaMemcpyAsync(dF, F, (size_t)n * p * 8, cudaMemcpyHostToDevice, s_main));
+    if (p > 0) CUDA_CHECK(cudaMemcpyAsync(dF, F, (size_t)n * p * 8, cudaMemcpyHostToDevice, s_main));
     if (noise && dnoise) CUDA_CHECK(cudaMemcpyAsync(dnoise, noise, (size_t)n * 8, cudaMemcpyHostToDevice, s_main));
     CUDA_CHECK(cudaStreamSynchronize(s_main));
     have_model = have_W = have_V = have_x = false;
@@ -987,18 +1002,18 @@ struct Engine {
     for (int q0 = 0; q0 < nrhs; q0 += WAVE_MAX_RHS) {
       const int nq = std::min(WAVE_MAX_RHS, nrhs - q0);
       double* Bq = B + (long long)q0 * N;
-      dev_zero_ints(wave_ctl, nb + 1);
-      ++launches;
+      launches += 2;
+      wave_reset_kernel<<<(unsigned)(((long long)N * nq + 255) / 256), 256, 0, s_main>>>(wave_ctl, wave_z, (long long)N * nq);
       const CUtensorMap* mL = BWD ? mapA.wb : mapA.wf;
       const CUtensorMap* mW = BWD ? mapW.wb : mapW.wf;
       if (nq == 1)
-        trsv_wave_kernel<BWD, 1><<<grid, WAVE_THREADS, wave_smem_bytes(1), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, 0);
+        trsv_wave_kernel<BWD, 1><<<grid, WAVE_THREADS, wave_smem_bytes(1), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, wave_z, 0);
       else if (nq == 2)
-        trsv_wave_kernel<BWD, 2><<<grid, WAVE_THREADS, wave_smem_bytes(2), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, 0);
+        trsv_wave_kernel<BWD, 2><<<grid, WAVE_THREADS, wave_smem_bytes(2), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, wave_z, 0);
       else if (nq <= 4)
-        trsv_wave_kernel<BWD, 4><<<grid, WAVE_THREADS, wave_smem_bytes(4), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, 0);
+        trsv_wave_kernel<BWD, 4><<<grid, WAVE_THREADS, wave_smem_bytes(4), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, wave_z, 0);
       else
-        trsv_wave_kernel<BWD, 8><<<grid, WAVE_THREADS, wave_smem_bytes(8), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, 0);
+        trsv_wave_kernel<BWD, 8><<<grid, WAVE_THREADS, wave_smem_bytes(8), s_main>>>(mL, mW, Bq, N, nq, nb, wave_ctl, wave_z, 0);
       CUDA_CHECK(cudaGetLastError());
     }
   }
@@ -1194,6 +1209,27 @@ struct Engine {
     CUDA_CHECK(cudaGetLastError());
   }
 
+  // ---- ladder shortcut: set the accepted factor aside while a lower rung is tried (Engine::eval) ----
+  // The factor lives in A (L), W's diagonal blocks (their inverses) and logdet_blocks.  A and V swap roles (V is
+  // scratch until TRTRI), the two small pieces are copied.
+  double *ladder_D = nullptr, *ladder_logdet = nullptr;
+  void stash_factor() {
+    if (!ladder_D) {
+      ladder_D = dalloc<double>((size_t)nb * BLK * BLK);
+      ladder_logdet = dalloc<double>(nb);
+    }
+    copy_diag_blocks(ladder_D, BLK, (long long)BLK * BLK, W, ld, (long long)BLK * ld + BLK);
+    dev_copy(ladder_logdet, logdet_blocks, nb);
+    std::swap(A, V);
+    std::swap(mapA, mapV);
+  }
+  void unstash_factor() {
+    std::swap(A, V);
+    std::swap(mapA, mapV);
+    copy_diag_blocks(W, ld, (long long)BLK * ld + BLK, ladder_D, BLK, (long long)BLK * BLK);
+    dev_copy(logdet_blocks, ladder_logdet, nb);
+  }
+
   void tic(int idx) { CUDA_CHECK(cudaEventRecord(ev_t[idx], s_main)); }
 
   // deterministic sum of squares of a vector (n rows) into dscal[slot]
@@ -1355,36 +1391,53 @@ struct Engine {
     if (!updated) {
       // Ladder shortcut (lkgpu_set_ladder_shortcut, on by default; LKGPU_FULL_LADDER=1 turns it off).  When the
       // previous evaluation on this handle was accepted on rung k >= 2 -- the optimiser is walking through the
-      // numerically singular region and every evaluation would climb k + 1 rungs = k + 1 full factorisations -- the
-      // ladder is entered at rung k - 1: rejected there (the expected case) it continues upwards as usual, 2
-      // factorisations instead of k + 1, under the one assumption that acceptance is monotone in the jitter (a rung
-      // below a rejected one is rejected).  If rung k - 1 is accepted instead, the assumption says nothing about the
-      // rungs below: the whole ladder is run from rung 0, exactly as without the shortcut.
+      // numerically singular region, where the plain ladder costs k + 1 full factorisations per evaluation -- the
+      // ladder is entered AT rung k, under the one assumption that acceptance is monotone in the jitter (a rung below
+      // a rejected one is rejected):
+      //  * rung k rejected: climb on from k + 1 as usual (the rungs below are rejected by the assumption);
+      //  * rung k accepted: the accepted factor is set aside (the A and V buffers swap roles; the inverted diagonal
+      //    blocks and the per-panel log-determinants are copied, 20 MB at n = 20000) and rung k - 1 is tried; while
+      //    that is accepted too the walk continues downwards; at the first rejection the lowest accepted factor is
+      //    taken back.  Usual case: 2 factorisations (k accepted, k - 1 rejected) instead of k + 1.
+      // The evaluation returns the n_jitter, the factor and the value of the plain ladder (tests: bit for bit).
       const int hint = ladder_shortcut ? last_n_jitter : 0;
-      int r = 0;
+      int r = 0, n_fact = 0;
       bool accepted = false;
+      auto try_rung = [&](int q, bool exact) {
+        ++n_fact;
+        return attempt(q, exact);
+      };
       if (hint >= 2) {
-        if (!attempt(hint - 1, false)) {
-          after_reject(hint - 1);
-          n_rungs_skipped = hint - 1;
-          r = hint;
-        } else {
-          for (r = 0; r < hint - 1 && !accepted; ++r) {
-            accepted = attempt(r, false);
-            if (!accepted) after_reject(r);
+        r = hint;
+        if (try_rung(r, false)) {
+          accepted = true;
+          while (r > 0) {
+            const double rc2_acc = rc2;
+            stash_factor();
+            if (try_rung(r - 1, false)) {  // also accepted: it replaces the one set aside
+              --r;
+              continue;
+            }
+            unstash_factor();
+            rc2 = rc2_acc;
+            break;
           }
-          if (accepted) --r;                       // the loop's ++r ran once more
-          else accepted = attempt(r = hint - 1, false);  // deterministic: accepted again, and A holds this factor
+          diag_add = ladder_diag(r);
+          have_W = false;
+        } else {
+          after_reject(r);
+          ++r;
         }
       }
       while (!accepted) {
-        accepted = attempt(r, need_inverse && r == 0 && last_n_jitter == 0);
+        accepted = try_rung(r, need_inverse && r == 0 && last_n_jitter == 0);
         if (!accepted) {
           after_reject(r);
           ++r;
         }
       }
       inc = r;
+      n_rungs_skipped = std::max(0, (r + 1) - n_fact);
     }
     if (need_inverse && !have_W) {
       // accepted on a later rung: L^-1 is formed once, after the ladder
@@ -1417,7 +1470,7 @@ struct Engine {
     {
       const long long tot = (long long)N * (p + 1);
       launches += 2;
-      pad_copy_kernel<<<(unsigned)(((long long)N * p + 255) / 256), 256, 0, s_main>>>(dF, n, n, p, Bv, N, N);
+      if (p > 0) pad_copy_kernel<<<(unsigned)(((long long)N * p + 255) / 256), 256, 0, s_main>>>(dF, n, n, p, Bv, N, N);
       pad_copy_kernel<<<(N + 255) / 256, 256, 0, s_main>>>(dy, n, n, 1, Bv + (long long)N * p, N, N);
       (void)tot;
       solve_fwd(Bv, p + 1);
@@ -1436,6 +1489,8 @@ struct Engine {
     CUDA_CHECK(cudaEventRecord(ev_t[6], s_main));
 
     int pdim = 0;
+    if ((objective == LKGPU_OBJ_LMP || objective == LKGPU_OBJ_LOO) && p == 0)
+      throw LkError{"LOO / LMP objectives need at least one trend column (regmodel 'none' is supported for LL only)"};
     if (objective == LKGPU_OBJ_LMP || objective == LKGPU_OBJ_LOO) lmp_loo_prepare(objective, pdim);
     CUDA_CHECK(cudaEventRecord(ev_t[7], s_main));
 
@@ -1546,13 +1601,13 @@ struct Engine {
         break;
       }
       case LKGPU_EXPORT_FSTAR:
-        CUDA_CHECK(cudaMemcpy2D(dst, (size_t)n * 8, Bv, (size_t)N * 8, (size_t)n * 8, p, cudaMemcpyDeviceToHost));
+        if (p > 0) CUDA_CHECK(cudaMemcpy2D(dst, (size_t)n * 8, Bv, (size_t)N * 8, (size_t)n * 8, p, cudaMemcpyDeviceToHost));
         break;
       case LKGPU_EXPORT_YSTAR:
         CUDA_CHECK(cudaMemcpy(dst, Bv + (long long)N * p, (size_t)n * 8, cudaMemcpyDeviceToHost));
         break;
       case LKGPU_EXPORT_RSTAR:
-        CUDA_CHECK(cudaMemcpy(dst, dRstar, (size_t)p * p * 8, cudaMemcpyDeviceToHost));
+        if (p > 0) CUDA_CHECK(cudaMemcpy(dst, dRstar, (size_t)p * p * 8, cudaMemcpyDeviceToHost));
         break;
       case LKGPU_EXPORT_ESTAR:
         CUDA_CHECK(cudaMemcpy(dst, Ev, (size_t)n * 8, cudaMemcpyDeviceToHost));
@@ -1562,7 +1617,7 @@ struct Engine {
         break;
       case LKGPU_EXPORT_Z:
         // m_z (Kriging.cpp:2168-2172): Estar when beta is estimated, ystar - Fstar beta when it is fixed
-        if (!has_fixed_beta) {
+        if (!has_fixed_beta || p == 0) {
           CUDA_CHECK(cudaMemcpy(dst, Ev, (size_t)n * 8, cudaMemcpyDeviceToHost));
         } else {
           std::vector<double> fs((size_t)n * p);
@@ -1724,7 +1779,7 @@ const char* lkgpu_last_error(void) { return g_last_error.c_str(); }
 int lkgpu_create(void** handle, int device, int n, int d, int p, const double* X, const double* y, const double* F,
                  const double* noise, int kernel, int noise_model) {
   LK_TRY
-  if (!handle || !X || !y || !F) throw LkError{"lkgpu_create: null argument"};
+  if (!handle || !X || !y || (!F && p > 0)) throw LkError{"lkgpu_create: null argument"};
   *handle = nullptr;
   Engine* e = new Engine();
   try {
@@ -1750,7 +1805,7 @@ int lkgpu_set_numerics(void* handle, double num_nugget, int max_inc_choldiag, do
 
 int lkgpu_set_data(void* handle, const double* X, const double* y, const double* F, const double* noise) {
   LK_TRY
-  if (!handle || !X || !y || !F) throw LkError{"lkgpu_set_data: null argument"};
+  if (!handle || !X || !y || (!F && static_cast<Engine*>(handle)->p > 0)) throw LkError{"lkgpu_set_data: null argument"};
   Engine* e = static_cast<Engine*>(handle);
   CUDA_CHECK(cudaSetDevice(e->device));
   e->set_data(X, y, F, noise);
@@ -1760,7 +1815,8 @@ int lkgpu_set_data(void* handle, const double* X, const double* y, const double*
 int lkgpu_append_data(void* handle, int n_u, const double* X_u, const double* y_u, const double* F_u,
                       const double* noise_u) {
   LK_TRY
-  if (!handle || !X_u || !y_u || !F_u) throw LkError{"lkgpu_append_data: null argument"};
+  if (!handle || !X_u || !y_u || (!F_u && static_cast<Engine*>(handle)->p > 0))
+    throw LkError{"lkgpu_append_data: null argument"};
   static_cast<Engine*>(handle)->append(n_u, X_u, y_u, F_u, noise_u);
   LK_CATCH
 }
@@ -1861,7 +1917,8 @@ int lkgpu_export(void* handle, int which, double* dst) {
 int lkgpu_predict(void* handle, int m, const double* Xn, const double* Fn, const double* beta, double r_on_factor,
                   double* mean_out, double* var_out) {
   LK_TRY
-  if (!handle || !Xn || !Fn || !beta || !mean_out) throw LkError{"lkgpu_predict: null argument"};
+  if (!handle || !Xn || !mean_out || ((!Fn || !beta) && static_cast<Engine*>(handle)->p > 0))
+    throw LkError{"lkgpu_predict: null argument"};
   static_cast<Engine*>(handle)->predict(m, Xn, Fn, beta, r_on_factor, mean_out, var_out);
   LK_CATCH
 }
@@ -1886,6 +1943,13 @@ int lkgpu_mem_info(int device, unsigned long long* free_bytes, unsigned long lon
   *total_bytes = t;
   LK_CATCH
 }
+
+#ifdef LKGPU_POTF2_PROFILE
+// debug builds only (tools/potf2_phases.py): clock64() stamps of the last panel kernel that ran
+int lkgpu_debug_potf2_profile(long long* out32) {
+  return cudaMemcpyFromSymbol(out32, lk::g_potf2_prof, 32 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int lkgpu_probe_fp64_peak(int device, int mode, double* tflops) {
   LK_TRY

@@ -271,10 +271,26 @@ gemm_dmma_kernel(const CUtensorMap* tmapM, const CUtensorMap* tmapN, const GemmA
   for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
     TileDesc td = gemm_get_tile(args, tile);
     double acc[4][8][2];
+    double* Cbase = args.C + (long long)(td.c_col + warp * 32 + g) * args.ldc + td.c_row + 2 * t;
+    if (args.epilogue == EPI_SUB) {
+      // C -= M N^T: the accumulators START at -C (loads issued here, in the shadow of the first TMA round trip) and
+      // the epilogue stores -acc: no read-modify-write latency at the end of the tile, where nothing hides it.
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {
+        const double* Ccol = Cbase + (long long)(8 * i) * args.ldc;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 8; ++j) {
+          const double2 c = *reinterpret_cast<const double2*>(Ccol + 8 * j);
+          acc[i][j][0] = -c.x;
+          acc[i][j][1] = -c.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
 
     for (int k0 = td.k_begin; k0 < td.k_end; k0 += TK) {
       if (is_producer) produce_one();
@@ -331,31 +347,17 @@ gemm_dmma_kernel(const CUtensorMap* tmapM, const CUtensorMap* tmapN, const GemmA
       }
     }
 
-    // ---- epilogue ----
-    double* Cbase = args.C + (long long)(td.c_col + warp * 32 + g) * args.ldc + td.c_row + 2 * t;
+    // ---- epilogue: C = acc (EPI_SET) | C = -acc (EPI_SETNEG, and EPI_SUB whose accumulators started at -C) ----
+    const double sgn = (args.epilogue == EPI_SET) ? 1.0 : -1.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       double* Ccol = Cbase + (long long)(8 * i) * args.ldc;
-      if (args.epilogue == EPI_SUB) {
-        double2 old[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) old[j] = *reinterpret_cast<const double2*>(Ccol + 8 * j);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          double2 v;
-          v.x = old[j].x - acc[i][j][0];
-          v.y = old[j].y - acc[i][j][1];
-          *reinterpret_cast<double2*>(Ccol + 8 * j) = v;
-        }
-      } else {
-        const double sgn = (args.epilogue == EPI_SETNEG) ? -1.0 : 1.0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          double2 v;
-          v.x = sgn * acc[i][j][0];
-          v.y = sgn * acc[i][j][1];
-          *reinterpret_cast<double2*>(Ccol + 8 * j) = v;
-        }
+      for (int j = 0; j < 8; ++j) {
+        double2 v;
+        v.x = sgn * acc[i][j][0];
+        v.y = sgn * acc[i][j][1];
+        *reinterpret_cast<double2*>(Ccol + 8 * j) = v;
       }
     }
   }

@@ -158,7 +158,7 @@ cov_rect_kernel(const double* __restrict__ X, int n, int d, const double* __rest
     for (int k = 0; k < d; ++k) {
       const double dx = X[(long long)k * n + i] - Xn[(long long)k * m + j];
       zero = zero && (fabs(dx) <= 2.220446049250313e-16);
-      corr_accum<KERNEL>(dx * kp.inv_theta[k], es, pr);
+      corr_accum<KERNEL>(dx * (kp.inv_theta[k] * corr_scale<KERNEL>()), es, pr);
     }
     v = zero ? 1.0 : corr_finish<KERNEL>(es, pr) * factor;
   }
@@ -375,7 +375,7 @@ void Engine::predict(int m, const double* Xn, const double* Fn, const double* be
   SweepGate gate(*this);
   for (int k = 0; k < d; ++k) kp.inv_theta[k] = 1.0 / last_theta[k];
   std::vector<double> hRstar((size_t)p * p);
-  CUDA_CHECK(cudaMemcpy(hRstar.data(), dRstar, (size_t)p * p * 8, cudaMemcpyDeviceToHost));
+  if (p > 0) CUDA_CHECK(cudaMemcpy(hRstar.data(), dRstar, (size_t)p * p * 8, cudaMemcpyDeviceToHost));
   const int chunk_max = 1024;
   double* dXn = dalloc<double>((size_t)std::min(m, chunk_max) * d);
   double* dS = dalloc<double>((size_t)N * std::min(m, chunk_max));

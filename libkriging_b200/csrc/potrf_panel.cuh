@@ -33,6 +33,15 @@ constexpr int POTF2_SMEM_BYTES = POTF2_SMEM_DOUBLES * 8;
 
 __device__ __forceinline__ int potf2_blk(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
 
+// -DLKGPU_POTF2_PROFILE: thread 0 stamps clock64() at the phase boundaries of the panel kernel (read back with
+// lkgpu_debug_potf2_profile; tools/potf2_phases.py).  Not compiled into the product library.
+#ifdef LKGPU_POTF2_PROFILE
+__device__ long long g_potf2_prof[32];
+#define POTF2_STAMP(k) do { if (threadIdx.x == 0) g_potf2_prof[k] = clock64(); } while (0)
+#else
+#define POTF2_STAMP(k) do { } while (0)
+#endif
+
 __device__ __forceinline__ void potf2_bar(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
@@ -79,11 +88,13 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
     if (s_abort != 0) return;
   }
 
+  POTF2_STAMP(0);
   for (int idx = tid; idx < 128 * 64; idx += POTF2_THREADS) {
     const int c = idx >> 6, r2 = (idx & 63) * 2;
     *reinterpret_cast<double2*>(As + c * 128 + r2) = *reinterpret_cast<const double2*>(Ablk + (long long)c * ld + r2);
   }
   __syncthreads();
+  POTF2_STAMP(1);
 
   bool ok = true;
   for (int kb = 0; kb < 4; ++kb) {
@@ -136,6 +147,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
       potf2_invert_diag(Ldt + ((kb - 1) & 1) * 1024, rdiag + c0 - 32, Xb + potf2_blk(kb - 1, kb - 1) * 1024, lane);
     }
     __syncthreads();
+    POTF2_STAMP(2 + 2 * kb);
     const int R0 = c0 + 32;
     const int m = 128 - R0;  // rows / columns left after this sub-panel
     if (m > 0) {
@@ -172,6 +184,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
       }
       __syncthreads();
     }
+    POTF2_STAMP(3 + 2 * kb);
   }
 
   // failure flag (NaN-safe: piv > 0 is false for NaN; every thread of rows 0..127 saw every pivot) and the block's
@@ -193,6 +206,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
     *reinterpret_cast<double2*>(Ablk + (long long)c * ld + r2) = v;
   }
 
+  POTF2_STAMP(10);
   // ---------------- off-diagonal blocks of the inverse, one block sub-diagonal at a time ----------------
   // T_ij = sum_{k=j}^{i-1} L_ik X_kj  is parked in As's upper block (j, i);  X_ij = -X_ii T_ij.
   for (int dd = 1; dd < 4; ++dd) {
@@ -225,6 +239,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
     __syncthreads();
   }
 
+  POTF2_STAMP(11);
   // write the inverse into W's diagonal block (strict upper zero)
   double* Wblk = W + (long long)jb * ld + jb;
   for (int idx = tid; idx < 128 * 64; idx += POTF2_THREADS) {
@@ -234,6 +249,7 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
     if (i >= j) v = *reinterpret_cast<const double2*>(Xb + potf2_blk(i, j) * 1024 + (c & 31) * 32 + (r2 & 31));
     *reinterpret_cast<double2*>(Wblk + (long long)c * ld + r2) = v;
   }
+  POTF2_STAMP(12);
 }
 
 }  // namespace lk

@@ -11,8 +11,15 @@
 // CTAs take row blocks from a ticket counter in sweep order, so a CTA only ever waits on blocks owned by CTAs
 // that are already resident (no deadlock for any grid size).  Each CTA streams ITS row (column) of 128 x 128
 // tiles through a TMA ring as fast as HBM delivers them -- L is read-only, so the prefetch never waits -- and
-// consumes tile j as soon as the flag of z_j is published (st.release / ld.acquire at gpu scope).  The serial
-// chain per block is then: see flag -> one tile product -> one Dinv product -> publish  (~3-4 us).
+// consumes tile j as soon as z_j is published.  Publication is by VALUE: the solution blocks go to a scratch vector
+// Zpub that the host pre-fills with a sentinel bit pattern (a NaN payload no computation produces; computed NaNs
+// are canonicalised before the store), and each consumer thread polls its own element with ld.relaxed.gpu until it
+// is not the sentinel -- one L2 round trip from the producer's store to the consumer's register, no flag, no fence
+// (every 8-byte element is published and consumed on its own).  The serial chain per block is then:
+// see z_j -> one tile product -> one Dinv product -> store z_i.  (Round 1 published a flag per block with
+// st.release after a __threadfence and re-read the block after the acquire: three dependent L2 round trips and a
+// gpu-scope fence per step, ~4 us x nb steps per sweep -- the sweep was bound by that chain, not by HBM:
+// profiles/r02_side_kernels.md.)
 //
 // Tile traffic: forward uses boxes {128 rows, 32 cols} (dense, thread <-> row: conflict-free LDS.64),
 // backward uses boxes {16 rows, 128 cols} with SWIZZLE_128B (thread <-> column: conflict-free LDS.128).
@@ -57,11 +64,25 @@ __device__ __forceinline__ void bar_sync_compute() {
   asm volatile("bar.sync 1, %0;" ::"n"(WAVE_COMPUTE_THREADS) : "memory");
 }
 
-// ctl[0] = ticket counter, ctl[1 + i] = flag of row block i (zeroed by the host before each launch).
+constexpr unsigned long long WAVE_SENTINEL = 0xFFF85EA71E5EA711ull;  // "not yet published"
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const double* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// before each launch: ticket counter = 0, Zpub[0 .. count) = sentinel
+__global__ void wave_reset_kernel(int* __restrict__ ctl, double* __restrict__ zpub, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) ctl[0] = 0;
+  if (i < count) zpub[i] = __longlong_as_double((long long)WAVE_SENTINEL);
+}
+
+// ctl[0] = ticket counter; Zpub = [nrhs][ldb] published solution blocks (see above).
 template <bool BWD, int NQ>
 __global__ void __launch_bounds__(WAVE_THREADS, 1)
 trsv_wave_kernel(const CUtensorMap* tmapL, const CUtensorMap* tmapW,  // tensor maps in device memory
-                 double* __restrict__ B, long long ldb, int nrhs, int nb, int* __restrict__ ctl, int sched_fence) {
+                 double* __restrict__ B, long long ldb, int nrhs, int nb, int* __restrict__ ctl,
+                 double* __restrict__ Zpub, int sched_fence) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the shared array (not through an integer cast): the compiler keeps
   // the shared address space, so the tile / vector reads below are LDS, not generic loads.
@@ -87,7 +108,6 @@ trsv_wave_kernel(const CUtensorMap* tmapL, const CUtensorMap* tmapW,  // tensor 
     tma_prefetch_desc(tmapL);
     tma_prefetch_desc(tmapW);
   }
-  int* flags = ctl + 1;
   int stage = 0;
   uint32_t phase = 0;
 
@@ -140,14 +160,24 @@ trsv_wave_kernel(const CUtensorMap* tmapL, const CUtensorMap* tmapW,  // tensor 
       const bool diag = (tq == ntiles - 1);
       if (!diag) {
         const int j = BWD ? (nb - 1 - tq) : tq;
-        if (tid == 0) {
-          while (ld_acquire_gpu(flags + j) == 0) {
-          }
-        }
-        bar_sync_compute();
+        double zj[NQ];
         if (tid < 128) {
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) vec[q * 128 + tid] = (q < nrhs) ? ld_relaxed_gpu_f64(B + q * ldb + j * 128 + tid) : 0.0;
+          for (int q = 0; q < NQ; ++q) {
+            zj[q] = 0.0;
+            if (q < nrhs) {
+              unsigned long long bits;
+              do {
+                bits = ld_relaxed_gpu_u64(Zpub + q * ldb + j * 128 + tid);
+              } while (bits == WAVE_SENTINEL);
+              zj[q] = __longlong_as_double((long long)bits);
+            }
+          }
+        }
+        bar_sync_compute();  // everybody is done with the previous tile's vec
+        if (tid < 128) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) vec[q * 128 + tid] = zj[q];
         }
         bar_sync_compute();
       } else {
@@ -215,11 +245,14 @@ trsv_wave_kernel(const CUtensorMap* tmapL, const CUtensorMap* tmapW,  // tensor 
     if (h == 0) {
 #pragma unroll
       for (int q = 0; q < NQ; ++q)
-        if (q < nrhs) st_relaxed_gpu_f64(B + q * ldb + ib + r, part[q * 128 + r] + part[(NQ + q) * 128 + r]);
-      __threadfence();
+        if (q < nrhs) {
+          double z = part[q * 128 + r] + part[(NQ + q) * 128 + r];
+          if (z != z) z = __longlong_as_double(0x7FF8000000000000ll);  // never the sentinel
+          st_relaxed_gpu_f64(Zpub + q * ldb + ib + r, z);  // published: consumers poll this element
+          B[q * ldb + ib + r] = z;                          // the result
+        }
     }
-    bar_sync_compute();
-    if (tid == 0) st_release_gpu(flags + i, 1);
+    bar_sync_compute();  // part[] is reused by the next row block
   }
 }
 

@@ -26,7 +26,7 @@ def build() -> bool:
 
 def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL", regmodel="constant", normalize=False,
         mode="eval", optim="none", theta=None, gamma=None, grad=True, sigma2=None, est_sigma2=None, nugget=None,
-        est_nugget=None, Xn=None, device=0, timeout=None, update=None):
+        est_nugget=None, Xn=None, device=0, timeout=None, update=None, concurrent_starts=None, beta=None):
     """Run lkgpu::Kriging on (X, y): mode='fit' (optim=BFGS[#]) or 'eval' (objective value / gradient at theta or
     gamma).  Returns the driver's JSON (theta, beta, sigma2, nugget, objective_at_fit, pred_mean, pred_sd, ...)."""
     if not available():
@@ -51,6 +51,12 @@ def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL",
             cfg["sigma2"] = repr(float(sigma2)); cfg["est_sigma2"] = int(bool(est_sigma2))
         if nugget is not None:
             cfg["nugget"] = repr(float(nugget)); cfg["est_nugget"] = int(bool(est_nugget))
+        if concurrent_starts is not None:
+            cfg["concurrent_starts"] = int(concurrent_starts)
+        if beta is not None:
+            b = np.ascontiguousarray(beta, dtype=np.float64).ravel()
+            cfg["beta_n"] = b.size
+            b.tofile(os.path.join(wd, "beta.bin"))
         if Xn is not None:
             Xn = np.asfortranarray(Xn, dtype=np.float64)
             cfg["m"] = Xn.shape[0]

@@ -59,7 +59,13 @@ int main(int argc, char** argv) {
     using NM = lkgpu::Kriging::NoiseModel;
     const NM nm = noise_model == "nugget" ? NM::Nugget : noise_model == "hetero" ? NM::Heterogeneous : NM::None;
     lkgpu::Kriging k(kernel, nm, device);
+    if (cfg.count("concurrent_starts")) k.set_concurrent_starts(geti("concurrent_starts", 0));
     lkgpu::Kriging::Parameters prm;
+    if (geti("beta_n", 0) > 0) {  // fixed trend coefficients (Parameters::beta, is_beta_estim = false)
+      const int bn = geti("beta_n", 0);
+      prm.beta = arma::vec(read_bin(wd + "/beta.bin", bn).data(), bn);
+      prm.is_beta_estim = false;
+    }
     if (exists(wd + "/theta.bin")) prm.theta = arma::mat(read_bin(wd + "/theta.bin", (size_t)nt * d).data(), nt, d);
     if (cfg.count("sigma2")) { prm.sigma2 = getd("sigma2", 1.0); prm.is_sigma2_estim = geti("est_sigma2", 0) != 0; }
     if (cfg.count("nugget")) { prm.nugget = getd("nugget", 0.0); prm.is_nugget_estim = geti("est_nugget", 0) != 0; }
@@ -68,7 +74,8 @@ int main(int argc, char** argv) {
     const double t0 = now_s();
     if (nm == NM::Heterogeneous) k.fit(y, noise, X, regmodel, normalize, mode == "fit" ? optim : "none", objective, prm);
     else k.fit(y, X, regmodel, normalize, mode == "fit" ? optim : "none", objective, prm);
-    js << "\"fit_s\": " << (now_s() - t0) << ", \"n_eval\": " << k.n_eval() << ", ";
+    js << "\"fit_s\": " << (now_s() - t0) << ", \"n_eval\": " << k.n_eval() << ", \"concurrent_starts\": "
+       << k.last_concurrency() << ", ";
     if (mode == "eval") {
       const int gd = d + (nm == NM::None ? 0 : 1);
       arma::vec gamma = exists(wd + "/gamma.bin") ? arma::vec(read_bin(wd + "/gamma.bin", gd).data(), gd)

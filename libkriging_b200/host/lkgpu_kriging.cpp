@@ -4,11 +4,15 @@
 // formulas.  The objective itself (populate_Model + reductions) is one lkgpu_objective_fun call.
 #include "lkgpu_kriging.hpp"
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <random>
 #include <stdexcept>
+#include <thread>
 
 #include "../../include/lkgpu.h"
 #include "lbfgsb_cpp/lbfgsb.hpp"
@@ -22,6 +26,13 @@ namespace lkgpu {
 
 namespace {
 constexpr double NUGGET_ALPHA_LOWER = 1e-3;  // Kriging.cpp:678
+
+// The f2c'd Lbfgsb.3.0 (dependencies/lbfgsb_cpp/Lbfgsb.3.0/{lbfgsb,linpack,blas}.c) keeps its scratch variables in
+// `static` locals, so setulb must never run on two threads at once (all state that persists between its calls lives
+// in the optimiser's own wa / iwa / *save arrays).  Concurrent multistart workers therefore hold this mutex whenever
+// they are inside lbfgsb::Optimizer::minimize and drop it only for the duration of an objective evaluation -- the
+// part that runs on the GPU and is worth overlapping.
+std::mutex g_lbfgsb_mutex;
 
 void check(int rc) {
   if (rc != 0) throw std::runtime_error(lkgpu_last_error());
@@ -129,14 +140,35 @@ void Kriging::push_params() {
 }
 
 double Kriging::objective(int obj, const arma::vec& gamma, arma::vec* grad) {
-  double val = 0.0;
-  arma::vec g(gamma.n_elem, arma::fill::zeros);
-  check(lkgpu_objective_fun(m_h, obj, gamma.memptr(), (int)gamma.n_elem, grad != nullptr, &val,
-                            grad ? g.memptr() : nullptr, nullptr));
-  if (grad) *grad = g;
   m_have_scalars = false;  // the device now holds the model at gamma
   ++m_n_eval;
+  return objective_on(m_h, obj, gamma, grad);
+}
+
+double Kriging::objective_on(void* h, int obj, const arma::vec& gamma, arma::vec* grad) const {
+  double val = 0.0;
+  arma::vec g(gamma.n_elem, arma::fill::zeros);
+  check(lkgpu_objective_fun(h, obj, gamma.memptr(), (int)gamma.n_elem, grad != nullptr, &val,
+                            grad ? g.memptr() : nullptr, nullptr));
+  if (grad) *grad = g;
   return val;
+}
+
+// Number of engine handles with overlapping evaluations for this process's multistart rows (the batched-occupancy
+// path of BASELINE cfg 5): a factorisation of n <= 8192 cannot fill 148 SMs, so such fits keep several starts in
+// flight, one handle and one host thread each.  set_concurrent_starts(K) overrides; results do not depend on it.
+int Kriging::concurrency(int n_starts, arma::uword n) const {
+  int want = m_concurrent_starts > 0 ? m_concurrent_starts : (n <= 3072 ? 8 : (n <= 8192 ? 4 : 1));
+  want = std::max(1, std::min(want, n_starts));
+  if (want > 1) {
+    unsigned long long free_b = 0, total_b = 0;
+    if (lkgpu_mem_info(m_device, &free_b, &total_b) == 0) {
+      const unsigned long long N = (n + 127) / 128 * 128;
+      const unsigned long long per = 3ull * 8ull * N * N + (64ull << 20);
+      want = std::max(1, std::min<int>(want, 1 + (int)(0.7 * (double)free_b / (double)per)));
+    }
+  }
+  return want;
 }
 
 void Kriging::model_scalars(const arma::vec& theta, double extra, double* SSE, arma::vec* betahat) {
@@ -215,7 +247,8 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
   if (noise) m_noise = *noise;  // stored raw even when normalize = true (quirk (iii))
   m_F = regression_model_matrix(regmodel, m_X);
   const arma::uword p = m_F.n_cols;
-  if (p == 0) throw std::runtime_error("regmodel='none' (no trend column) is not supported by the device engine");
+  if (p == 0 && obj != LKGPU_OBJ_LL)
+    throw std::runtime_error("regmodel='none' (no trend column) is supported for objective='LL' only");
   m_est_beta = true;
   if (!prm.is_beta_estim && prm.beta.has_value() && prm.beta->n_elem > 0) {
     m_est_beta = false;
@@ -348,10 +381,19 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
   push_params();
 
   const double sign = obj == LKGPU_OBJ_LOO ? 1.0 : -1.0;
-  auto fit_ofn = [&](const arma::vec& gamma, arma::vec* grad_out) -> double {
+  // fit_ofn on engine handle h; `locked`: the caller holds g_lbfgsb_mutex, which is dropped while the device works
+  auto fit_ofn = [&](void* h, const arma::vec& gamma, arma::vec* grad_out, bool locked) -> double {
     const arma::vec v = reparam_from(gamma);
     arma::vec g;
-    const double val = objective(obj, v, grad_out ? &g : nullptr);
+    if (locked) g_lbfgsb_mutex.unlock();
+    double val;
+    try {
+      val = objective_on(h, obj, v, grad_out ? &g : nullptr);
+    } catch (...) {
+      if (locked) g_lbfgsb_mutex.lock();
+      throw;
+    }
+    if (locked) g_lbfgsb_mutex.lock();
     if (grad_out) *grad_out = sign * reparam_deriv(v, g);
     return sign * val;
   };
@@ -361,12 +403,12 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
                                               : config.objective_rel_tolerance / 1e-13;
 
   // ---- one L-BFGS-B run per start (optimize_worker, Kriging.cpp:1904-2084) ----
-  for (arma::uword s = 0; s < multistart; ++s) {
-    if ((int)(s % (arma::uword)m_world) != m_rank) continue;
+  auto optimize_worker = [&](arma::uword s, void* h) -> StartResult {
     StartResult res;
     res.start_index = (int)s;
     res.objective_value = std::numeric_limits<double>::infinity();
-    const int eval0 = m_n_eval;
+    int n_eval = 0;
+    std::unique_lock<std::mutex> lk(g_lbfgsb_mutex);
     try {
       const arma::vec theta_start = starts.row(s % multistart).t();
       arma::vec full = theta_start;
@@ -389,8 +431,11 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
       arma::vec best_gamma = gamma_tmp;
       while (retry <= config.max_restart) {
         auto r = optimizer.minimize(
-            [&](const arma::vec& x, arma::vec& grad) -> double { return fit_ofn(x, &grad); }, gamma_tmp,
-            lo_loc.memptr(), up_loc.memptr(), bounds_type.data());
+            [&](const arma::vec& x, arma::vec& grad) -> double {
+              ++n_eval;
+              return fit_ofn(h, x, &grad, true);
+            },
+            gamma_tmp, lo_loc.memptr(), up_loc.memptr(), bounds_type.data());
         if (r.f_opt < best_f) {
           best_f = r.f_opt;
           best_gamma = gamma_tmp;
@@ -413,7 +458,8 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
           break;
         }
       }
-      res.objective_value = fit_ofn(best_gamma, nullptr);  // final evaluation (Kriging.cpp:2044)
+      ++n_eval;
+      res.objective_value = fit_ofn(h, best_gamma, nullptr, true);  // final evaluation (Kriging.cpp:2044)
       res.gamma = best_gamma;
       res.success = true;
       res.retries = retry;
@@ -421,9 +467,49 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
       res.success = false;
       res.error_message = e.what();
     }
-    res.n_eval = m_n_eval - eval0;
-    m_results.push_back(res);
+    res.n_eval = n_eval;
+    return res;
+  };
+
+  // this process's starts: {s : s mod world == rank}, several of them in flight when n is mid-size
+  std::vector<arma::uword> mine;
+  for (arma::uword s = 0; s < multistart; ++s)
+    if ((int)(s % (arma::uword)m_world) == m_rank) mine.push_back(s);
+  const int ncon = concurrency((int)mine.size(), n);
+  m_last_concurrency = ncon;
+  std::vector<StartResult> results(mine.size());
+  if (ncon <= 1) {
+    for (size_t k = 0; k < mine.size(); ++k) results[k] = optimize_worker(mine[k], m_h);
+  } else {
+    // one engine handle (own workspaces, own CUDA streams) and one host thread per start in flight
+    std::vector<void*> handles{m_h};
+    try {
+      for (int w = 1; w < ncon; ++w) {
+        void* h = nullptr;
+        check(lkgpu_create(&h, m_device, (int)n, (int)d, (int)p, m_X.memptr(), m_y.memptr(), m_F.memptr(),
+                           noise ? m_noise.memptr() : nullptr, kernel_id(m_kernel), (int)m_noise_model));
+        handles.push_back(h);
+        check(lkgpu_set_params(h, m_est_sigma2, m_sigma2, m_est_nugget, m_nugget, m_alpha));
+      }
+      std::atomic<size_t> next{0};
+      std::vector<std::thread> pool;
+      for (int w = 0; w < ncon; ++w)
+        pool.emplace_back([&, w]() {
+          for (size_t k = next.fetch_add(1); k < mine.size(); k = next.fetch_add(1))
+            results[k] = optimize_worker(mine[k], handles[w]);
+        });
+      for (auto& t : pool) t.join();
+    } catch (...) {
+      for (size_t w = 1; w < handles.size(); ++w) lkgpu_destroy(handles[w]);
+      throw;
+    }
+    for (size_t w = 1; w < handles.size(); ++w) lkgpu_destroy(handles[w]);
   }
+  for (const StartResult& r : results) {
+    m_n_eval += r.n_eval;
+    m_results.push_back(r);
+  }
+  m_have_scalars = false;
 
   if (m_world > 1) return;  // the caller exchanges start_results() and calls commit(gamma*)
   // ---- argmin over successful starts, strict '<' in start order (Kriging.cpp:2097-2114) ----

@@ -57,6 +57,11 @@ class Kriging {
   // multistart sharding: this process runs the starts {s : s mod world == rank}; the caller
   // exchanges start_results() (16 B per start) and calls commit(gamma*) on every rank.
   void set_shard(int rank, int world) { m_rank = rank; m_world = world; }
+  // Multistart rows in flight on this process's GPU (0 = by size: 8 for n <= 3072, 4 for n <= 8192, else 1).  One
+  // engine handle and one host thread per row in flight; the L-BFGS-B code itself (not thread-safe: f2c statics)
+  // runs under a process-wide mutex that is released for the duration of every objective evaluation.
+  void set_concurrent_starts(int k) { m_concurrent_starts = k; }
+  int last_concurrency() const { return m_last_concurrency; }
 
   void fit(const arma::vec& y, const arma::mat& X, const std::string& regmodel = "constant", bool normalize = false,
            const std::string& optim = "BFGS", const std::string& objective = "LL", const Parameters& parameters = Parameters());
@@ -95,6 +100,8 @@ class Kriging {
   void fit_impl(const arma::vec& y, const arma::vec* noise, const arma::mat& X, const std::string& regmodel,
                 bool normalize, const std::string& optim, const std::string& objective, const Parameters& prm);
   double objective(int obj, const arma::vec& gamma, arma::vec* grad);
+  double objective_on(void* h, int obj, const arma::vec& gamma, arma::vec* grad) const;
+  int concurrency(int n_starts, arma::uword n) const;
   void model_scalars(const arma::vec& theta, double extra, double* SSE, arma::vec* betahat);
   void push_params();
   void need_model();
@@ -107,7 +114,7 @@ class Kriging {
 
   std::string m_kernel, m_objective = "LL", m_regmodel = "constant";
   NoiseModel m_noise_model;
-  int m_device, m_rank = 0, m_world = 1;
+  int m_device, m_rank = 0, m_world = 1, m_concurrent_starts = 0, m_last_concurrency = 1;
   void* m_h = nullptr;
   bool m_is_empty = true, m_normalize = false;
   bool m_est_beta = true, m_est_sigma2 = true, m_est_nugget = true, m_est_theta = true, m_used_block = false;

@@ -39,7 +39,8 @@ class GpuBackend:
         self._scalars_key = None
         self._scalars = None
         # running totals over this handle's objective calls (bench.py reports them for the fit)
-        self.stats = dict(evals=0, jitter_rungs=0, device_ms=0.0, reject_info=0, reject_rcond=0, chol_ms=0.0, rcond_ms=0.0)
+        self.stats = dict(evals=0, jitter_rungs=0, device_ms=0.0, reject_info=0, reject_rcond=0, rungs_skipped=0,
+                          chol_ms=0.0, rcond_ms=0.0)
 
     def set_params(self, est_sigma2, sigma2, est_nugget, nugget, alpha):
         self.engine.set_params(est_sigma2, sigma2, est_nugget, nugget, alpha)
@@ -60,6 +61,7 @@ class GpuBackend:
         st["device_ms"] += float(info["stage_ms"]["total"])
         st["reject_info"] += int(info.get("reject_info", 0))
         st["reject_rcond"] += int(info.get("reject_rcond", 0))
+        st["rungs_skipped"] += int(info.get("rungs_skipped", 0))
         st["chol_ms"] += float(info["stage_ms"]["chol"])
         st["rcond_ms"] += float(info["stage_ms"]["rcond"])
         return val, grad
@@ -267,11 +269,12 @@ class Kriging:
         self.m_noise = noise  # stored raw even when normalize=True (quirk (iii))
         self.m_F = regression_model_matrix(regmodel, self.m_X)
         p = self.m_F.shape[1]
-        if p == 0:
-            raise NotImplementedError("regmodel='none' (no trend column) is not supported by the device engine")
+        if p == 0 and objective != "LL":
+            raise NotImplementedError("regmodel='none' (no trend column) is supported for objective='LL' only")
         is_beta_estim = parameters.get("is_beta_estim", True)
         beta = parameters.get("beta")
         self.m_est_beta = True
+        self.m_beta = np.zeros(0)
         if (not is_beta_estim) and beta is not None and np.size(beta) > 0:
             self.m_est_beta = False
             self.m_beta = np.asarray(beta, dtype=np.float64).ravel() / (self.m_scaleY if normalize else 1.0)

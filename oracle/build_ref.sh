@@ -18,7 +18,8 @@ OB="$SP/opencv_python_headless.libs"
 OBLIB=$(ls "$OB" | grep '^libopenblas' | head -1)
 if [ -z "$OBLIB" ]; then echo "[build_ref] no LP64 OpenBLAS found under $OB"; exit 1; fi
 mkdir -p "$OUT/obj"
-if [ "$OUT/ref_driver" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/ref_driver" -nt "$HERE/build_ref.sh" ]; then
+if [ "$OUT/ref_driver" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/ref_driver" -nt "$HERE/build_ref.sh" ] && \
+   [ "$OUT/ref_nested_driver" -nt "$HERE/ref_nested_driver.cpp" ] && [ "$OUT/ref_nested_driver" -nt "$HERE/build_ref.sh" ]; then
   echo "[build_ref] up to date"; exit 0
 fi
 cat > "$OUT/obj/version_stub.cpp" <<'EOS'
@@ -38,6 +39,14 @@ g++ $CXXFLAGS $INC -c "$OUT/obj/version_stub.cpp" -o "$OUT/obj/version_stub.o" &
 pids+=($!)
 g++ $CXXFLAGS $INC -c "$HERE/ref_driver.cpp" -o "$OUT/obj/ref_driver.o" &
 pids+=($!)
+# NestedKriging and what it links against, for ref_nested_driver
+mkdir -p "$OUT/obj_nested"
+for f in NestedKriging WarpKriging; do
+  g++ $CXXFLAGS $INC -c "$REF/src/lib/$f.cpp" -o "$OUT/obj_nested/$f.o" &
+  pids+=($!)
+done
+g++ $CXXFLAGS $INC -c "$HERE/ref_nested_driver.cpp" -o "$OUT/obj_nested/ref_nested_driver.o" &
+pids+=($!)
 for f in blas lbfgsb linpack s_cmp s_copy timer; do
   gcc -O2 -fPIC -w -Ddcopy_=Wcopy_ -Ddscal_=Wscal_ -Ddaxpy_=Waxpy_ -Ddnrm2_=Wnrm2_ -Dddot_=Wdot_ \
       -I"$REF/dependencies/lbfgsb_cpp/Lbfgsb.3.0" -I"$REF/dependencies/lbfgsb_cpp/Lbfgsb.3.0/include" \
@@ -45,6 +54,8 @@ for f in blas lbfgsb linpack s_cmp s_copy timer; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
+objs=$(ls "$OUT"/obj/*.o | grep -v '/ref_driver.o$')
+g++ -fopenmp -o "$OUT/ref_nested_driver" $objs "$OUT"/obj_nested/*.o -L"$OB" -l:"$OBLIB" -Wl,-rpath,"$OB" -Wl,-rpath,"$SP/scipy.libs" -lpthread
 g++ -fopenmp -o "$OUT/ref_driver" "$OUT"/obj/*.o -L"$OB" -l:"$OBLIB" -Wl,-rpath,"$OB" -Wl,-rpath,"$SP/scipy.libs" -lpthread
 echo "$OB:$SP/scipy.libs" > "$OUT/ld_library_path.txt"
 echo "[build_ref] built $OUT/ref_driver"

@@ -135,6 +135,8 @@ def safe_chol_lower(R: np.ndarray, num: Numerics | None = None):
 
 
 def solve_lower(L, B):
+    if np.size(B) == 0:  # regmodel "none": F has no column
+        return np.array(B, dtype=float, copy=True)
     x, info = lapack.dtrtrs(L, B, lower=1, trans=0)
     assert info == 0
     return x
@@ -257,14 +259,17 @@ def populate_model(pb: Problem, theta, extra=None) -> KModel:
     m.Rinv = solve_upper_Lt(m.L, solve_lower(m.L, np.eye(n)))
     m.Fstar = solve_lower(m.L, pb.F)
     m.ystar = solve_lower(m.L, pb.y)
-    G = m.Fstar.T @ m.Fstar
-    Rs, info = lapack.dpotrf(G, lower=0, clean=1)
-    if info != 0:
-        raise RuntimeError("chol(F*'F*) failed")
-    m.Rstar = Rs
-    rhs = m.Fstar.T @ m.ystar
-    t = lapack.dtrtrs(Rs, rhs, lower=0, trans=1)[0]
-    m.betahat = lapack.dtrtrs(Rs, t, lower=0, trans=0)[0]
+    if pb.F.shape[1] == 0:  # regmodel "none" (Trend.cpp:39): no trend, Rstar and betahat are empty
+        m.Rstar, m.betahat = np.zeros((0, 0)), np.zeros(0)
+    else:
+        G = m.Fstar.T @ m.Fstar
+        Rs, info = lapack.dpotrf(G, lower=0, clean=1)
+        if info != 0:
+            raise RuntimeError("chol(F*'F*) failed")
+        m.Rstar = Rs
+        rhs = m.Fstar.T @ m.ystar
+        t = lapack.dtrtrs(Rs, rhs, lower=0, trans=1)[0]
+        m.betahat = lapack.dtrtrs(Rs, t, lower=0, trans=0)[0]
     resid = pb.y - pb.F @ m.betahat
     m.Estar = solve_lower(m.L, resid)
     m.SSEstar = float(m.Estar @ m.Estar)
@@ -566,7 +571,10 @@ def predict(pb: Problem, theta, sigma2, Xn, Fn, m: KModel | None = None, fixed_b
         beta = np.asarray(fixed_beta, float).ravel()
         z = m.ystar - m.Fstar @ beta
     mean = Fn @ beta + Rstar_on.T @ z
-    Ecirc = lapack.dtrtrs(m.Rstar, (Fn - Rstar_on.T @ m.Fstar).T, lower=0, trans=1)[0].T
+    if m.Rstar.size == 0:
+        Ecirc = np.zeros((Xn.shape[0], 0))
+    else:
+        Ecirc = lapack.dtrtrs(m.Rstar, (Fn - Rstar_on.T @ m.Fstar).T, lower=0, trans=1)[0].T
     var = 1.0 - np.sum(Rstar_on * Rstar_on, axis=0) + np.sum(Ecirc * Ecirc, axis=1)
     var = np.maximum(var, 0.0)
     return mean, np.sqrt(var * sigma2)

@@ -73,7 +73,7 @@ def main():
         c.update(value=r["value"], grad=r["grad"], eval_s=r["eval_s_all"][0], populate_s=r["fit_s"],
                  wall_s=time.time() - t0, threads=threads, y_sum=float(np.sum(y)), X_sum=float(np.sum(X)))
         res[name] = c
-        print(name, r["value"], r["grad"][:3], "eval_s", r["eval_s_all"], flush=True)
+        print(name, repr(r["value"]), r["grad"], "eval_s", r["eval_s_all"], flush=True)
         with open(OUT, "w") as f:
             json.dump(dict(source="oracle/_ref/ref_driver (unmodified libKriging, OpenBLAS 0.3.15, %d threads), "
                                   "logLikelihoodFun / leaveOneOutFun / logMargPostFun(theta, grad=true) after "

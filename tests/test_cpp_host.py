@@ -105,3 +105,29 @@ def test_cpp_host_objective_matches_ctypes_path():
         v, g = e.objective("LL", th, True)
     assert r["value"] == v
     assert np.array_equal(np.array(r["grad"]), g)
+
+
+@pytest.mark.gpu
+def test_cpp_host_concurrent_starts_equal_sequential():
+    """lkgpu::Kriging::set_concurrent_starts: a BFGS6 fit with 4 multistart rows in flight (one engine handle and one
+    host thread each, L-BFGS-B itself under the process-wide mutex) is bit for bit the sequential fit."""
+    X, y, _ = synth(900, 4, 71, "smooth")
+    rs = [host.run(X, y, kernel="matern5_2", mode="fit", optim="BFGS6", concurrent_starts=k) for k in (1, 4, 4)]
+    assert [r["concurrent_starts"] for r in rs] == [1, 4, 4]
+    for r in rs[1:]:
+        assert r["theta"] == rs[0]["theta"] and r["sigma2"] == rs[0]["sigma2"] and r["n_eval"] == rs[0]["n_eval"]
+        assert r["objective_at_fit"] == rs[0]["objective_at_fit"]
+
+
+@pytest.mark.gpu
+def test_cpp_host_fixed_beta_matches_reference():
+    """Parameters{beta, is_beta_estim=false} through the C++ host (tests/golden/refgen_fixed_beta.json)."""
+    for c in json.load(open(os.path.join(GOLDEN, "refgen_fixed_beta.json")))["cases"]:
+        X, y, _ = synth(c["n"], c["d"], c["seed"], "smooth")
+        Xn = np.random.Generator(np.random.PCG64(c["seed"] + 1000)).random((20, c["d"]))
+        r = host.run(X, y, kernel=c["kernel"], regmodel=c["regmodel"], normalize=c["normalize"], mode="fit",
+                     optim=c["optim"], theta=np.array(c["theta"])[None, :], beta=c["beta"], Xn=Xn)
+        tol = 1e-9 if c["optim"] == "none" else 1e-5
+        assert relerr_vec(r["beta"], c["beta_out"]) < 1e-14
+        assert relerr_vec(r["pred_mean"], c["pred_mean"]) < tol, c["name"]
+        assert relerr_vec(r["pred_sd"], c["pred_sd"]) < tol * 10, c["name"]

@@ -125,3 +125,23 @@ def test_gpu_fixed_beta_matches_reference(c):
     assert relerr_vec(mean, c["pred_mean"]) < tol
     assert relerr_vec(sd, c["pred_sd"]) < tol * 10
     k.close()
+
+
+def test_gpu_regmodel_none_matches_reference():
+    """regmodel = "none" (Trend.cpp:39: no trend column, p = 0): fit, objective and predict against reference runs
+    (tests/golden/refgen_none_trend.json)."""
+    import json
+    import os
+    from tests.util import GOLDEN
+    for c in json.load(open(os.path.join(GOLDEN, "refgen_none_trend.json")))["cases"]:
+        X, y, _ = synth(c["n"], c["d"], c["seed"], "smooth")
+        k = Kriging(c["kernel"])
+        k.fit(y, X, "none", False, c["optim"], "LL", parameters={"theta": np.full((1, c["d"]), c["theta0"])})
+        tol = 1e-9 if c["optim"] == "none" else 1e-6
+        assert relerr(k.theta(), c["theta"]) < tol and relerr(k.sigma2(), c["sigma2"]) < 10 * tol
+        assert k.beta().size == 0
+        assert relerr(k.logLikelihood(), c["objective_at_fit"]) < tol
+        Xn = np.random.Generator(np.random.PCG64(c["seed"] + 1000)).random((20, c["d"]))
+        mean, sd = k.predict(Xn, True)
+        assert relerr_vec(mean, c["pred_mean"]) < 10 * tol and relerr_vec(sd, c["pred_sd"]) < 10 * tol
+        k.close()

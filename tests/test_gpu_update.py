@@ -52,8 +52,12 @@ def test_block_extension_equals_from_scratch(capi, no, nu, kernel, noise_model):
         # and against the oracle's restatement of the reference
         pb = ko.Problem(X=X, y=y, F=F, kernel=kernel, noise_model=noise_model, noise=nz)
         vo, go = ko.log_likelihood(pb, gamma, True)
-        assert relerr(v, vo) < 1e-10
-        assert relerr_vec(g, go) < 1e-9
+        # cond(R) reaches 4e8 in these cases: rounding the ENTRIES of R differently (1 ulp, as any two correct
+        # evaluations of the kernel do) moves the reference's own LL by 3e-10 relative -- measured with the oracle for
+        # the (640, 700) matern5_2 case -- so the gate against the oracle is 1e-9 here; the two device paths above,
+        # which share their R, are gated at 1e-10.
+        assert relerr(v, vo) < 1e-9
+        assert relerr_vec(g, go) < 1e-8
         # an evaluation at another point is a factorisation from scratch and drops the kept factor
         e.objective("LL", gamma * 1.1, False)
         assert not e.last_eval_was_update

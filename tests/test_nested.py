@@ -146,3 +146,41 @@ def test_batched_submodel_fits_on_device():
     assert np.all(theta > 0) and sigma2 > 0
     for k in list(seq.values()) + list(bat.values()):
         k.close()
+
+
+def _nested_reference_cases():
+    import json
+    import os
+    from tests.util import GOLDEN
+    return json.load(open(os.path.join(GOLDEN, "refgen_nested.json")))["cases"]
+
+
+def _check_against_reference_nested(c, backend_factory, tol, concurrent):
+    """Step 1 + step 2 of NestedKriging::fit (NestedKriging.cpp:262-331) on the partition the reference drew."""
+    X, y, _ = synth(c["n"], c["d"], c["seed"], "smooth")
+    groups = [np.array(g) for g in c["groups"]]
+    prm = {"theta": np.full((1, c["d"]), c["theta0"])} if "theta0" in c else None
+    kw = {"backend_factory": backend_factory} if backend_factory else {}
+    m = nested.fit_submodels(y, X, groups, c["kernel"], parameters=prm, concurrent=concurrent, **kw)
+    theta, sigma2, beta0 = nested.unify_hyperparameters(m, groups, y, X)
+    assert relerr(theta, c["theta"]) < tol and relerr(sigma2, c["sigma2"]) < tol and relerr(beta0, c["beta0"]) < tol
+    for g, sm in enumerate(c["submodels"]):
+        assert relerr(m[g].theta(), sm["theta"]) < tol and relerr(m[g].sigma2(), sm["sigma2"]) < tol
+        assert relerr(m[g].beta(), sm["beta"]) < tol
+        assert relerr(m[g].logLikelihood(), sm["LL"]) < max(tol, 1e-9)
+    for k in m.values():
+        k.close()
+
+
+@pytest.mark.parametrize("c", _nested_reference_cases(), ids=lambda c: c["name"])
+def test_nested_matches_reference_nestedkriging_host(c):
+    """Host logic (oracle as backend) against the UNMODIFIED reference's NestedKriging (tests/golden/refgen_nested.json,
+    generated by oracle/_ref/ref_nested_driver): sub-model fits + unified hyper-parameters within 1e-6."""
+    _check_against_reference_nested(c, OracleBackend, 1e-6, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", _nested_reference_cases(), ids=lambda c: c["name"])
+def test_nested_matches_reference_nestedkriging_device(c):
+    """The same with the device engine, all sub-model fits in flight at once."""
+    _check_against_reference_nested(c, None, 1e-6, 8)

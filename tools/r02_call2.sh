@@ -15,7 +15,7 @@ import json
 for f in ("gpurun_out/r02c2/bench.json","gpurun_out/r02c2/bench_full_ladder.json"):
     try:
         j=json.loads(open(f).read().strip().splitlines()[-1]); ft=j["fit"]
-        print(f, "wall", ft["wall_s"], "evals", ft["n_eval_all_ranks"], "obj", ft["objective_at_fit"], "theta0", ft["theta"][:3], ft["ladder"])
+        print(f, "wall", ft["wall_s"], "evals", ft["n_eval_all_ranks"], "LL", ft["LL_at_fit"], "theta0", ft["theta"][:3], ft["ladder"])
     except Exception as e: print(f, "failed", e)
 PY
 echo "== concurrency experiments (n=5000 d=20 gauss)"
