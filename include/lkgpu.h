@@ -174,13 +174,16 @@ int lkgpu_restore_model(void* handle);
  * Schur complement is exhausted.  An evaluation at any other point factors from scratch and drops the kept factor. */
 int lkgpu_append_data(void* handle, int n_u, const double* X_u, const double* y_u, const double* F_u,
                       const double* noise_u);
-/* safe_chol_lower's ladder (src/lib/LinearAlgebra.cpp:68-98) climbs from rung 0 on every call: an evaluation that
- * is accepted after k diagonal bumps costs k + 1 factorisations.  With the shortcut (default on; flag = 0 or the
- * environment variable LKGPU_FULL_LADDER=1 restore the plain ladder) an evaluation on a handle whose PREVIOUS
- * evaluation was accepted on rung k >= 2 enters the ladder at rung k: rejected there it climbs on as usual; accepted
- * there, the factor is set aside and the rungs below are tried downwards until one is rejected (usually the first:
- * 2 factorisations instead of k + 1).  Same n_jitter, same factor, same value as the plain ladder whenever
- * acceptance is monotone in the jitter.  stage_ms[LKGPU_CT_RUNGS_SKIPPED] counts the factorisations saved. */
+/* safe_chol_lower's ladder (src/lib/LinearAlgebra.cpp:68-98) returns the LOWEST accepted rung by trying rung 0, 1,
+ * 2, ...: k + 1 factorisations when the answer is k.  With the shortcut (default on; flag = 0 or the environment
+ * variable LKGPU_FULL_LADDER=1 restore the plain ladder) the same rung is searched as the step of a monotone function:
+ * first probe = the rung the previous evaluation on this handle accepted, further probes predicted from the rcond of
+ * the last attempt inside the bracket (rejected, accepted), an accepted factor being set aside while a lower rung is
+ * tried.  2-3 factorisations instead of k + 1; same n_jitter, factor and value as the plain ladder WHENEVER acceptance
+ * is monotone in the jitter.  It is not always: in the numerically singular regime a low rung can be "accepted" by
+ * rounding luck while a higher one is rejected (DESIGN.md documents a case); a caller that needs the plain ladder's
+ * decision there turns the shortcut off.  An evaluation on a fresh handle always runs the plain ladder.
+ * stage_ms[LKGPU_CT_RUNGS_SKIPPED] counts the factorisations saved. */
 int lkgpu_set_ladder_shortcut(void* handle, int flag);
 /* 1 if the last evaluation on this handle ran as a block extension of a kept factor, else 0 */
 int lkgpu_last_eval_was_update(void* handle);

@@ -267,6 +267,7 @@ struct Engine {
   bool have_model = false, have_W = false, have_V = false, have_x = false;
   double last_alpha = 1.0, last_inv_sigma2 = 0.0, last_diag_add = 0.0;
   int last_n_jitter = 0;
+  long long evals_done = 0;  // evaluations completed on this handle since its data were set (ladder shortcut history)
   std::vector<double> last_theta;
   // factor kept across lkgpu_append_data (the reference's m_T while m_X has more rows than m_T)
   int keep_n = 0;
@@ -615,6 +616,7 @@ struct Engine {
     }
     free_old();
     have_model = have_W = have_V = have_x = have_loo = false;
+    evals_done = 0;
   }
 
   void set_data(const double* X, const double* y, const double* F, const double* noise) {
@@ -624,6 +626,7 @@ struct Engine {
     if (noise && dnoise) CUDA_CHECK(cudaMemcpyAsync(dnoise, noise, (size_t)n * 8, cudaMemcpyHostToDevice, s_main));
     CUDA_CHECK(cudaStreamSynchronize(s_main));
     have_model = have_W = have_V = have_x = false;
+    evals_done = 0;
     keep_n = 0;
     cm.valid = false;
     live_is_committed = false;
@@ -1389,55 +1392,65 @@ struct Engine {
         throw LkError{"[ERROR] Cannot add numerical nugget which is not strictly positive: " + std::to_string(num_nugget)};
     };
     if (!updated) {
-      // Ladder shortcut (lkgpu_set_ladder_shortcut, on by default; LKGPU_FULL_LADDER=1 turns it off).  When the
-      // previous evaluation on this handle was accepted on rung k >= 2 -- the optimiser is walking through the
-      // numerically singular region, where the plain ladder costs k + 1 full factorisations per evaluation -- the
-      // ladder is entered AT rung k, under the one assumption that acceptance is monotone in the jitter (a rung below
-      // a rejected one is rejected):
-      //  * rung k rejected: climb on from k + 1 as usual (the rungs below are rejected by the assumption);
-      //  * rung k accepted: the accepted factor is set aside (the A and V buffers swap roles; the inverted diagonal
-      //    blocks and the per-panel log-determinants are copied, 20 MB at n = 20000) and rung k - 1 is tried; while
-      //    that is accepted too the walk continues downwards; at the first rejection the lowest accepted factor is
-      //    taken back.  Usual case: 2 factorisations (k accepted, k - 1 rejected) instead of k + 1.
-      // The evaluation returns the n_jitter, the factor and the value of the plain ladder (tests: bit for bit).
-      const int hint = ladder_shortcut ? last_n_jitter : 0;
-      int r = 0, n_fact = 0;
-      bool accepted = false;
-      auto try_rung = [&](int q, bool exact) {
+      // The ladder as a search.  safe_chol_lower returns the LOWEST accepted rung: it tries rung 0, 1, 2, ... and
+      // stops at the first acceptance, k + 1 full factorisations when the answer is k.  With the shortcut
+      // (lkgpu_set_ladder_shortcut, on by default; LKGPU_FULL_LADDER=1 turns it off) the same rung is found as the
+      // step of a monotone function -- the one assumption being that acceptance is monotone in the jitter (a rung
+      // below a rejected one is rejected, a rung above an accepted one is accepted):
+      //  * the first probe is the rung the previous evaluation on this handle accepted (an optimiser walking
+      //    through the numerically singular region stays near it);
+      //  * a bracket (lo rejected, hi accepted) is kept; the next probe is predicted from the rcond of the last
+      //    attempt -- rcond_1(L)^2 of R + j I grows about linearly with j once j dominates the smallest eigenvalue,
+      //    i.e. one decade per rung -- and clamped into the bracket; the search ends when hi = lo + 1;
+      //  * an accepted factor is set aside before a lower rung is tried (A and V swap roles; the inverted diagonal
+      //    blocks and per-panel log-determinants are copied, 20 MB at n = 20000) and taken back if that rung fails.
+      // Usual costs: 2 factorisations when the rung is unchanged (k accepted, k - 1 rejected), 2 when the point is
+      // well conditioned again (k accepted, 0 accepted), 3 when the rung jumps from 0 to k -- against k + 1.
+      // Without the shortcut the probes are 0, 1, 2, ...: the plain ladder, factorisation for factorisation.
+      // (a handle without history -- its first evaluation, or the first after new data -- runs the plain ladder)
+      const bool shortcut = ladder_shortcut && evals_done > 0;
+      const int hint = shortcut ? last_n_jitter : 0;
+      const int top = max_inc + 1;  // the last rung the reference tries (LinearAlgebra.cpp:75-90)
+      int lo = -1, hi = -1, n_fact = 0;
+      double rc_lo = NAN, rc_hi = NAN;
+      bool acc_in_stash = false;
+      int probe = hint >= 2 ? std::min(hint, top) : 0;
+      while (true) {
+        if (hi >= 0 && !acc_in_stash) {
+          stash_factor();
+          acc_in_stash = true;
+        }
+        rc2 = NAN;
         ++n_fact;
-        return attempt(q, exact);
-      };
-      if (hint >= 2) {
-        r = hint;
-        if (try_rung(r, false)) {
-          accepted = true;
-          while (r > 0) {
-            const double rc2_acc = rc2;
-            stash_factor();
-            if (try_rung(r - 1, false)) {  // also accepted: it replaces the one set aside
-              --r;
-              continue;
-            }
-            unstash_factor();
-            rc2 = rc2_acc;
-            break;
-          }
-          diag_add = ladder_diag(r);
-          have_W = false;
+        if (attempt(probe, need_inverse && probe == 0 && last_n_jitter == 0)) {
+          hi = probe;
+          rc_hi = rc2;
+          acc_in_stash = false;
         } else {
-          after_reject(r);
-          ++r;
+          if (hi < 0) after_reject(probe);  // throws where the reference's ladder ends
+          lo = probe;
+          rc_lo = rc2;
+        }
+        if (hi >= 0 && hi - lo == 1) break;
+        if (hi < 0) {
+          int up = 1;  // rungs to climb: predicted from how far below the threshold this rung's rcond^2 is
+          if (shortcut && std::isfinite(rc_lo) && rc_lo > 0.0 && rc_lo < min_rcond)
+            up = std::max(1, (int)std::ceil(std::log10(min_rcond / rc_lo)));
+          probe = std::min(lo + up, top);
+        } else {
+          int down = 1;  // rungs expected to be droppable: how far above the threshold the accepted rcond^2 is
+          if (std::isfinite(rc_hi) && rc_hi >= min_rcond) down = std::max(1, (int)std::floor(std::log10(rc_hi / min_rcond)));
+          probe = std::max(lo + 1, std::min(hi - 1, hi - down));
         }
       }
-      while (!accepted) {
-        accepted = try_rung(r, need_inverse && r == 0 && last_n_jitter == 0);
-        if (!accepted) {
-          after_reject(r);
-          ++r;
-        }
+      if (acc_in_stash) {
+        unstash_factor();
+        rc2 = rc_hi;
+        have_W = false;
       }
-      inc = r;
-      n_rungs_skipped = std::max(0, (r + 1) - n_fact);
+      inc = hi;
+      diag_add = ladder_diag(hi);
+      n_rungs_skipped = std::max(0, (hi + 1) - n_fact);
     }
     if (need_inverse && !have_W) {
       // accepted on a later rung: L^-1 is formed once, after the ladder
@@ -1551,6 +1564,7 @@ struct Engine {
     cudaEventElapsedTime(&t, ev_t[8], ev_t[9]); out->stage_ms[LKGPU_ST_GRAD] = t;
     cudaEventElapsedTime(&t, ev_t[0], ev_t[9]); out->stage_ms[LKGPU_ST_TOTAL] = t;
     have_model = true;
+    ++evals_done;
   }
 
   // LMP / LOO common: U = Rinv F LX^-T (n x p), S2, sum log diag LX.   (filled in lmp_loo.cuh)

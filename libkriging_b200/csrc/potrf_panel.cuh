@@ -53,14 +53,21 @@ __device__ __forceinline__ void potf2_invert_diag(const double* __restrict__ Ld,
   double x[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    double s0 = 0.0, s1 = 0.0;
+    // four partial sums: the dot product's dependent chain is i / 4 FMAs deep instead of i / 2
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-    for (int k = 0; k + 1 < i; k += 2) {
+    for (int k = 0; k + 3 < i; k += 4) {
       const double2 l = *reinterpret_cast<const double2*>(Ld + i * 32 + k);
+      const double2 m = *reinterpret_cast<const double2*>(Ld + i * 32 + k + 2);
       s0 = fma(l.x, x[k], s0);
       s1 = fma(l.y, x[k + 1], s1);
+      s2 = fma(m.x, x[k + 2], s2);
+      s3 = fma(m.y, x[k + 3], s3);
     }
-    if (i & 1) s0 = fma(Ld[i * 32 + i - 1], x[i - 1], s0);
+#pragma unroll
+    for (int k = i & ~3; k < i; ++k) s0 = fma(Ld[i * 32 + k], x[k], s0);
+    s0 = (s0 + s1) + (s2 + s3);
+    s1 = 0.0;
     const double rdi = rdiag_c0[i];
     x[i] = (i == lane) ? rdi : ((i > lane) ? -(s0 + s1) * rdi : 0.0);
     Xd[lane * 32 + i] = x[i];
@@ -89,9 +96,19 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
   }
 
   POTF2_STAMP(0);
-  for (int idx = tid; idx < 128 * 64; idx += POTF2_THREADS) {
-    const int c = idx >> 6, r2 = (idx & 63) * 2;
-    *reinterpret_cast<double2*>(As + c * 128 + r2) = *reinterpret_cast<const double2*>(Ablk + (long long)c * ld + r2);
+  {
+    // 128 x 128 doubles = 16 double2 per thread: all 16 loads are in flight before the first store
+    double2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int idx = tid + q * POTF2_THREADS;
+      v[q] = *reinterpret_cast<const double2*>(Ablk + (long long)(idx >> 6) * ld + (idx & 63) * 2);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int idx = tid + q * POTF2_THREADS;
+      *reinterpret_cast<double2*>(As + (idx >> 6) * 128 + (idx & 63) * 2) = v[q];
+    }
   }
   __syncthreads();
   POTF2_STAMP(1);
@@ -197,13 +214,18 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
   __syncthreads();
   if (tid == 0) logdet_blocks[blk_index] = ((logp[0] + logp[1]) + logp[2]) + logp[3];
 
-  // write L back (lower part incl. diagonal; strict upper zero)
-  for (int idx = tid; idx < 128 * 64; idx += POTF2_THREADS) {
-    const int c = idx >> 6, r2 = (idx & 63) * 2;
-    double2 v = *reinterpret_cast<const double2*>(As + c * 128 + r2);
-    if (r2 < c) v.x = 0.0;
-    if (r2 + 1 < c) v.y = 0.0;
-    *reinterpret_cast<double2*>(Ablk + (long long)c * ld + r2) = v;
+  // write L back (lower part incl. diagonal; strict upper zero) -- warps 0..14; meanwhile warp 15 inverts the last
+  // diagonal sub-block (the first three were inverted behind the column steps)
+  if (warp == 15) {
+    potf2_invert_diag(Ldt + 1024, rdiag + 96, Xb + potf2_blk(3, 3) * 1024, lane);
+  } else {
+    for (int idx = tid; idx < 128 * 64; idx += POTF2_THREADS - 32) {
+      const int c = idx >> 6, r2 = (idx & 63) * 2;
+      double2 v = *reinterpret_cast<const double2*>(As + c * 128 + r2);
+      if (r2 < c) v.x = 0.0;
+      if (r2 + 1 < c) v.y = 0.0;
+      *reinterpret_cast<double2*>(Ablk + (long long)c * ld + r2) = v;
+    }
   }
 
   POTF2_STAMP(10);
@@ -211,19 +233,22 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
   // T_ij = sum_{k=j}^{i-1} L_ik X_kj  is parked in As's upper block (j, i);  X_ij = -X_ii T_ij.
   for (int dd = 1; dd < 4; ++dd) {
     const int nblk = 4 - dd;
-    // the last diagonal sub-block's inverse is not needed by the T products of the first sub-diagonal
-    if (dd == 1 && warp == 15) potf2_invert_diag(Ldt + 1024, rdiag + 96, Xb + potf2_blk(3, 3) * 1024, lane);
     for (int e = tid; e < nblk * 1024; e += POTF2_THREADS) {
       const int b = e >> 10, rr = e & 31, cc = (e >> 5) & 31;
       const int j = b, i = b + dd;
-      double s = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four partial sums: short dependent chains
       for (int k = j; k < i; ++k) {
         const double* Lik = As + (32 * k) * 128 + 32 * i + rr;          // L[32i+rr, 32k+kk] = Lik[kk*128]
         const double* Xkj = Xb + potf2_blk(k, j) * 1024 + cc * 32;      // X[32k+kk, 32j+cc] = Xkj[kk]
-#pragma unroll 8
-        for (int kk = 0; kk < 32; ++kk) s = fma(Lik[kk * 128], Xkj[kk], s);
+#pragma unroll
+        for (int kk = 0; kk < 32; kk += 4) {
+          s0 = fma(Lik[kk * 128], Xkj[kk], s0);
+          s1 = fma(Lik[(kk + 1) * 128], Xkj[kk + 1], s1);
+          s2 = fma(Lik[(kk + 2) * 128], Xkj[kk + 2], s2);
+          s3 = fma(Lik[(kk + 3) * 128], Xkj[kk + 3], s3);
+        }
       }
-      As[(32 * i + cc) * 128 + 32 * j + rr] = s;  // T[rr, cc] in the upper block (j, i)
+      As[(32 * i + cc) * 128 + 32 * j + rr] = (s0 + s1) + (s2 + s3);  // T[rr, cc] in the upper block (j, i)
     }
     __syncthreads();
     for (int e = tid; e < nblk * 1024; e += POTF2_THREADS) {
@@ -231,10 +256,15 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
       const int j = b, i = b + dd;
       const double* Xii = Xb + potf2_blk(i, i) * 1024 + rr;              // X[32i+rr, 32i+kk] = Xii[kk*32]
       const double* T = As + (32 * i + cc) * 128 + 32 * j;               // T[kk, cc] = T[kk]
-      double s = 0.0;
-#pragma unroll 8
-      for (int kk = 0; kk < 32; ++kk) s = fma(Xii[kk * 32], T[kk], s);
-      Xb[potf2_blk(i, j) * 1024 + cc * 32 + rr] = -s;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+        s0 = fma(Xii[kk * 32], T[kk], s0);
+        s1 = fma(Xii[(kk + 1) * 32], T[kk + 1], s1);
+        s2 = fma(Xii[(kk + 2) * 32], T[kk + 2], s2);
+        s3 = fma(Xii[(kk + 3) * 32], T[kk + 3], s3);
+      }
+      Xb[potf2_blk(i, j) * 1024 + cc * 32 + rr] = -((s0 + s1) + (s2 + s3));
     }
     __syncthreads();
   }
