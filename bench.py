@@ -375,9 +375,11 @@ def gp_draw(_capi, X, y0, kernel, theta, device, seed=321):
     return y
 
 
-def fit_block(Kriging, cfg, X, y, optim, local, comm, world, max_over_ranks, barrier, torch, concurrent=None):
+def fit_block(Kriging, cfg, X, y, optim, local, comm, world, max_over_ranks, barrier, torch, concurrent=None,
+              ladder_shortcut=None):
     """One Kriging.fit through the host API; returns the `fit` dict incl. per-rank statistics and balance."""
-    k = Kriging(cfg["kernel"], cfg["noise_model"], device=local, concurrent_starts=concurrent)
+    k = Kriging(cfg["kernel"], cfg["noise_model"], device=local, concurrent_starts=concurrent,
+                ladder_shortcut=ladder_shortcut)
     barrier()
     t0 = time.perf_counter()
     k.fit(y, X, optim=optim, objective=cfg["objective"] if cfg["objective"] != "LOO" else "LL", comm=comm)
@@ -595,6 +597,7 @@ def run_b200_arm(args, cfg):
 
     # ---- fit wall time: Kriging.fit(BFGS<world>), one start per GPU, on a GP-draw y ----
     fit = None
+    fit_plain = None
     if not args.no_fit and cfg.get("fit"):
         if cfg["noise_model"] == "none":
             y_fit = gp_draw(_capi, X, y, cfg["kernel"], cfg["theta"], local)
@@ -606,6 +609,16 @@ def run_b200_arm(args, cfg):
         fit = fit_block(Kriging, cfg, X, y_fit, optim, local, comm, world, max_over_ranks, barrier, torch,
                         concurrent=cfg.get("handles"))
         fit["y"] = y_desc
+        fit["ladder_mode"] = ("shortcut: safe_chol_lower's lowest accepted rung found by a bracketed search from the "
+                              "previous evaluation's rung (lkgpu_set_ladder_shortcut, the engine's default)")
+        # the same fit with the reference's plain ladder (rung 0, 1, 2, ... on every evaluation): same model expected
+        if args.config == 2 and not args.no_plain_ladder:
+            fp = fit_block(Kriging, cfg, X, y_fit, optim, local, comm, world, max_over_ranks, barrier, torch,
+                           concurrent=cfg.get("handles"), ladder_shortcut=False)
+            fit_plain = {"wall_s": fp["wall_s"], "n_eval_all_ranks": fp["n_eval_all_ranks"], "LL_at_fit": fp["LL_at_fit"],
+                         "ladder": fp["ladder"], "theta_identical_to_fit": fp["theta"] == fit["theta"],
+                         "LL_identical_to_fit": fp["LL_at_fit"] == fit["LL_at_fit"],
+                         "n_eval_identical_to_fit": fp["n_eval_all_ranks"] == fit["n_eval_all_ranks"]}
 
     # ---- the same fit through the C++ host (lkgpu::Kriging: Armadillo API + lbfgsb_cpp loop on the CPU, every
     #      objective evaluation through the C ABI) -- the host north_star names; single process, this rank's GPU ----
@@ -741,6 +754,7 @@ def run_b200_arm(args, cfg):
         "cpu_baseline": cpu,
         "parity_vs_reference": parity,
         "fit": fit,
+        "fit_plain_ladder": fit_plain,
         "fit_cpp_host": fit_cpp,
         "batched": batched,
         "update": update,
@@ -768,6 +782,7 @@ def main():
     ap.add_argument("--no-update", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-cpp-host", action="store_true")
+    ap.add_argument("--no-plain-ladder", action="store_true", help="skip the second fit with the plain jitter ladder")
     ap.add_argument("--peak", default="cublas", choices=["cublas", "max"])
     ap.add_argument("--ref-budget", type=float, default=1300.0,
                     help="reference arm: seconds allowed for the full-size run (the driver's limit is 1800 s)")

@@ -176,13 +176,14 @@ int lkgpu_append_data(void* handle, int n_u, const double* X_u, const double* y_
                       const double* noise_u);
 /* safe_chol_lower's ladder (src/lib/LinearAlgebra.cpp:68-98) returns the LOWEST accepted rung by trying rung 0, 1,
  * 2, ...: k + 1 factorisations when the answer is k.  With the shortcut (default on; flag = 0 or the environment
- * variable LKGPU_FULL_LADDER=1 restore the plain ladder) the same rung is searched as the step of a monotone function:
- * first probe = the rung the previous evaluation on this handle accepted, further probes predicted from the rcond of
- * the last attempt inside the bracket (rejected, accepted), an accepted factor being set aside while a lower rung is
- * tried.  2-3 factorisations instead of k + 1; same n_jitter, factor and value as the plain ladder WHENEVER acceptance
- * is monotone in the jitter.  It is not always: in the numerically singular regime a low rung can be "accepted" by
- * rounding luck while a higher one is rejected (DESIGN.md documents a case); a caller that needs the plain ladder's
- * decision there turns the shortcut off.  An evaluation on a fresh handle always runs the plain ladder.
+ * variable LKGPU_FULL_LADDER=1 restore the plain ladder) an evaluation on a handle whose PREVIOUS evaluation was
+ * accepted on rung k >= 2 probes rung k first: rejected, it climbs on from k + 1; accepted, the factor is set aside and
+ * the rungs below are tried downwards until one is rejected (rung 0 first when the rcond of rung k says the
+ * un-jittered matrix should pass: if rung 0 is accepted the answer is 0 unconditionally).  Usually 2 factorisations
+ * instead of k + 1; same n_jitter, factor and value as the plain ladder WHENEVER acceptance is monotone in the jitter
+ * below rung k.  It is not always: in the numerically singular regime a low rung can be "accepted" by rounding luck
+ * while a higher one is rejected (DESIGN.md documents a case); a caller that needs the plain ladder's decision there
+ * turns the shortcut off.  The first evaluation on a handle (or after new data) always runs the plain ladder.
  * stage_ms[LKGPU_CT_RUNGS_SKIPPED] counts the factorisations saved. */
 int lkgpu_set_ladder_shortcut(void* handle, int flag);
 /* 1 if the last evaluation on this handle ran as a block extension of a kept factor, else 0 */

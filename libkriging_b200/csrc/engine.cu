@@ -1392,28 +1392,28 @@ struct Engine {
         throw LkError{"[ERROR] Cannot add numerical nugget which is not strictly positive: " + std::to_string(num_nugget)};
     };
     if (!updated) {
-      // The ladder as a search.  safe_chol_lower returns the LOWEST accepted rung: it tries rung 0, 1, 2, ... and
-      // stops at the first acceptance, k + 1 full factorisations when the answer is k.  With the shortcut
-      // (lkgpu_set_ladder_shortcut, on by default; LKGPU_FULL_LADDER=1 turns it off) the same rung is found as the
-      // step of a monotone function -- the one assumption being that acceptance is monotone in the jitter (a rung
-      // below a rejected one is rejected, a rung above an accepted one is accepted):
-      //  * the first probe is the rung the previous evaluation on this handle accepted (an optimiser walking
-      //    through the numerically singular region stays near it);
-      //  * a bracket (lo rejected, hi accepted) is kept; the next probe is predicted from the rcond of the last
-      //    attempt -- rcond_1(L)^2 of R + j I grows about linearly with j once j dominates the smallest eigenvalue,
-      //    i.e. one decade per rung -- and clamped into the bracket; the search ends when hi = lo + 1;
-      //  * an accepted factor is set aside before a lower rung is tried (A and V swap roles; the inverted diagonal
-      //    blocks and per-panel log-determinants are copied, 20 MB at n = 20000) and taken back if that rung fails.
-      // Usual costs: 2 factorisations when the rung is unchanged (k accepted, k - 1 rejected), 2 when the point is
-      // well conditioned again (k accepted, 0 accepted), 3 when the rung jumps from 0 to k -- against k + 1.
-      // Without the shortcut the probes are 0, 1, 2, ...: the plain ladder, factorisation for factorisation.
+      // Ladder shortcut (lkgpu_set_ladder_shortcut, on by default; LKGPU_FULL_LADDER=1 turns it off).
+      // safe_chol_lower returns the LOWEST accepted rung by trying rung 0, 1, 2, ...: k + 1 full factorisations when
+      // the answer is k.  With the shortcut the first probe is the rung k >= 2 the previous evaluation on this handle
+      // accepted (an optimiser walking through the numerically singular region stays near it):
+      //  * rung k rejected: the ladder climbs on from k + 1, one rung at a time;
+      //  * rung k accepted: the factor is set aside (A and V swap roles; the inverted diagonal blocks and per-panel
+      //    log-determinants are copied, 20 MB at n = 20000) and the rungs below are tried downwards, one at a time,
+      //    until one is rejected; the lowest accepted factor is taken back;
+      //  * rung k accepted with an rcond so far above the threshold that the un-jittered matrix is expected to pass
+      //    (rcond_1(L)^2 of R + j I grows about one decade per rung once j dominates the smallest eigenvalue): rung 0
+      //    is probed first -- if it is accepted the answer is 0, which is the plain ladder's answer UNCONDITIONALLY
+      //    (it tries rung 0 first), and a point that has left the singular region costs 2 factorisations, not k + 1.
+      // Usual cost: 2 factorisations (k accepted, k - 1 rejected) instead of k + 1.  The result is the plain ladder's
+      // whenever acceptance is monotone in the jitter below rung k (see DESIGN.md for the one observed exception).
+      // Without the shortcut, and with a hint below 2, the probes are 0, 1, 2, ...: the plain ladder itself.
       // (a handle without history -- its first evaluation, or the first after new data -- runs the plain ladder)
       const bool shortcut = ladder_shortcut && evals_done > 0;
       const int hint = shortcut ? last_n_jitter : 0;
       const int top = max_inc + 1;  // the last rung the reference tries (LinearAlgebra.cpp:75-90)
       int lo = -1, hi = -1, n_fact = 0;
-      double rc_lo = NAN, rc_hi = NAN;
-      bool acc_in_stash = false;
+      double rc_hi = NAN;
+      bool acc_in_stash = false, probed_zero = false;
       int probe = hint >= 2 ? std::min(hint, top) : 0;
       while (true) {
         if (hi >= 0 && !acc_in_stash) {
@@ -1429,18 +1429,16 @@ struct Engine {
         } else {
           if (hi < 0) after_reject(probe);  // throws where the reference's ladder ends
           lo = probe;
-          rc_lo = rc2;
         }
         if (hi >= 0 && hi - lo == 1) break;
         if (hi < 0) {
-          int up = 1;  // rungs to climb: predicted from how far below the threshold this rung's rcond^2 is
-          if (shortcut && std::isfinite(rc_lo) && rc_lo > 0.0 && rc_lo < min_rcond)
-            up = std::max(1, (int)std::ceil(std::log10(min_rcond / rc_lo)));
-          probe = std::min(lo + up, top);
+          probe = lo + 1;  // climb, one rung at a time (after_reject has thrown where the reference's ladder ends)
+        } else if (lo < 0 && hi > 1 && !probed_zero && std::isfinite(rc_hi) &&
+                   rc_hi >= min_rcond * std::pow(10.0, hi)) {
+          probe = 0;       // the un-jittered matrix is expected to pass: if it does, 0 is the plain ladder's answer
+          probed_zero = true;
         } else {
-          int down = 1;  // rungs expected to be droppable: how far above the threshold the accepted rcond^2 is
-          if (std::isfinite(rc_hi) && rc_hi >= min_rcond) down = std::max(1, (int)std::floor(std::log10(rc_hi / min_rcond)));
-          probe = std::max(lo + 1, std::min(hi - 1, hi - down));
+          probe = hi - 1;  // walk down, one rung at a time
         }
       }
       if (acc_in_stash) {

@@ -89,6 +89,9 @@ class GpuBackend:
     def set_fixed_beta(self, beta):
         self.engine.set_fixed_beta(beta)
 
+    def set_ladder_shortcut(self, flag):
+        self.engine.set_ladder_shortcut(flag)
+
     def commit(self):
         """The model of the last evaluation becomes the committed one (Kriging.cpp:2156-2173)."""
         self.engine.commit_model()
@@ -185,7 +188,8 @@ class Kriging:
     NoiseKriging == noise_model="hetero" (reference Kriging.hpp:45-49)."""
 
     def __init__(self, kernel: str, noise_model: str = "none", *, device: int | None = None, backend_factory=None,
-                 concurrent_starts: int | None = None, concurrent_handle: bool = False):
+                 concurrent_starts: int | None = None, concurrent_handle: bool = False,
+                 ladder_shortcut: bool | None = None):
         if kernel not in ("gauss", "exp", "matern3_2", "matern5_2"):
             raise ValueError(f"Unsupported covariance kernel: {kernel}")
         nm = _NOISE_ALIASES.get(noise_model.lower())
@@ -199,6 +203,9 @@ class Kriging:
         self._concurrent_starts = concurrent_starts
         # True: this model is one of several being fitted at the same time on the device (nested.fit_submodels)
         self._concurrent_handle = bool(concurrent_handle)
+        # None: the engine's default (on; LKGPU_FULL_LADDER=1 turns it off).  False: safe_chol_lower's plain ladder on
+        # every evaluation (lkgpu_set_ladder_shortcut).
+        self._ladder_shortcut = ladder_shortcut
         self.config = _optim.OptimConfig.from_env()
         self.m_is_empty = True
         self.fit_log = {}
@@ -295,6 +302,8 @@ class Kriging:
                                                    self.m_noise, dev)
         if self._concurrent_handle and hasattr(be, "set_concurrent"):
             be.set_concurrent(True)
+        if self._ladder_shortcut is not None and hasattr(be, "set_ladder_shortcut"):
+            be.set_ladder_shortcut(self._ladder_shortcut)
         self.m_sigma2, self.m_nugget, self.m_alpha = 1.0, 0.0, 1.0
         self.m_is_empty = True
         sigma2_p = parameters.get("sigma2")
@@ -497,6 +506,8 @@ class Kriging:
                     b = self._backend_factory(self.m_X, self.m_y, self.m_F, self.m_kernel, self.m_noise_model,
                                               self.m_noise, dev)
                     b.set_params(self.m_est_sigma2, self.m_sigma2, self.m_est_nugget, self.m_nugget, self.m_alpha)
+                    if self._ladder_shortcut is not None and hasattr(b, "set_ladder_shortcut"):
+                        b.set_ladder_shortcut(self._ladder_shortcut)
                     extra_be.append(b)
                 with ThreadPoolExecutor(max_workers=ncon) as ex:
                     for f in [ex.submit(drain, b) for b in [be] + extra_be]:
