@@ -651,7 +651,7 @@ def run_b200_arm(args, cfg):
         thr = concurrent_throughput(_capi, X5, y5, c5, local, c5["handles"], 6, None, torch)
         thr_agg = sum_over_ranks(thr["evals"]) / max_over_ranks(thr["wall_s"])
         batched = {"workload": c5["name"], "throughput": thr, "evals_per_s_all_gpus": thr_agg}
-        if not args.no_fit:
+        if not args.no_fit and args.config != 5:  # (--config 5: that fit is the line's own `fit` block)
             y5f = gp_draw(_capi, X5, y5, c5["kernel"], c5["theta"], local)
             fb = fit_block(Kriging, c5, X5, y5f, f"BFGS{8 * world}", local, comm, world, max_over_ranks, barrier, torch,
                            concurrent=c5["handles"])
