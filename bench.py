@@ -621,27 +621,53 @@ def run_b200_arm(args, cfg):
                          "n_eval_identical_to_fit": fp["n_eval_all_ranks"] == fit["n_eval_all_ranks"]}
 
     # ---- the same fit through the C++ host (lkgpu::Kriging: Armadillo API + lbfgsb_cpp loop on the CPU, every
-    #      objective evaluation through the C ABI) -- the host north_star names; single process, this rank's GPU ----
+    #      objective evaluation through the C ABI) -- the host north_star names.  N = 1: one process on this GPU.
+    #      N > 1: rank 0 launches one C++ driver process per GPU; they share the multistart rows over lkgpu::ShardComm
+    #      (TCP star, no NCCL / MPI) while the Python ranks wait on the rendezvous store with their GPUs idle ----
     fit_cpp = None
-    if fit is not None and rank == 0 and not args.no_cpp_host and cfg["noise_model"] == "none":
-        try:
-            from libkriging_b200.host import driver as cpp
-            if cpp.available():
-                t0 = time.perf_counter()
-                r = cpp.run(X, y_fit, kernel=cfg["kernel"], objective="LL", mode="fit", optim="BFGS", device=local,
-                            timeout=900)
-                fit_cpp = {"host": "libkriging_b200/host/lkgpu_host_driver (C++: Armadillo + lbfgsb_cpp)",
-                           "wall_s": float(r["fit_s"]), "wall_s_incl_process_start": time.perf_counter() - t0,
-                           "n_eval": int(r["n_eval"]), "LL_at_fit": float(r["objective_at_fit"]),
-                           "theta": [float(t) for t in r["theta"]], "sigma2": float(r["sigma2"])}
-                if world == 1:
+    if fit is not None and not args.no_cpp_host and cfg["noise_model"] == "none":
+        barrier()
+        if rank == 0:
+            try:
+                from libkriging_b200.host import driver as cpp
+                if cpp.available():
+                    t0 = time.perf_counter()
+                    if world == 1:
+                        rs = [cpp.run(X, y_fit, kernel=cfg["kernel"], objective="LL", mode="fit", optim="BFGS",
+                                      device=local, timeout=900)]
+                    else:
+                        rs = cpp.run(X, y_fit, kernel=cfg["kernel"], objective="LL", mode="fit", optim=optim, timeout=1500,
+                                     world=world, devices=list(range(world)), concurrent_starts=cfg.get("handles"))
+                    r = rs[0]
+                    fit_cpp = {"host": "libkriging_b200/host/lkgpu_host_driver (C++: Armadillo + lbfgsb_cpp)",
+                               "processes": world, "optim": "BFGS" if world == 1 else optim,
+                               "wall_s": max(float(q["fit_s"]) for q in rs),
+                               "wall_s_incl_process_start": time.perf_counter() - t0,
+                               "n_eval": int(r["n_eval"]), "LL_at_fit": float(r["objective_at_fit"]),
+                               "theta": [float(t) for t in r["theta"]], "sigma2": float(r["sigma2"])}
+                    if world > 1:
+                        fit_cpp["exchange"] = ("lkgpu::ShardComm: tickets for the start queue + one all-gather of a row per "
+                                               "start over TCP (rank 0 serves); no GPU traffic")
+                        fit_cpp["per_rank"] = [{"rank": q["rank"], "device": q["device"], "fit_s": float(q["fit_s"]),
+                                                "evals": int(q["local_n_eval"]), "starts": q["local_starts"]} for q in rs]
+                        fit_cpp["all_ranks_same_model"] = all(q["theta"] == r["theta"] and q["sigma2"] == r["sigma2"]
+                                                              for q in rs)
                     th_py = np.asarray(fit["theta"])
                     fit_cpp["theta_relerr_vs_python_host"] = float(np.max(np.abs(np.asarray(r["theta"]) - th_py) / th_py))
                     fit_cpp["LL_relerr_vs_python_host"] = abs(fit_cpp["LL_at_fit"] - fit["LL_at_fit"]) / abs(fit["LL_at_fit"])
+                else:
+                    fit_cpp = {"unavailable": "libkriging_b200/host/_build/lkgpu_host_driver not built"}
+            except Exception as ex:  # pragma: no cover
+                fit_cpp = {"failed": str(ex)[:300]}
+        if world > 1:  # CPU-side wait (an NCCL barrier would keep a spinning kernel on the waiting GPUs)
+            from datetime import timedelta
+            from torch.distributed import distributed_c10d as c10d
+            st = c10d._get_default_store()
+            if rank == 0:
+                st.set("lkgpu/bench/cpp_fit_done", "1")
             else:
-                fit_cpp = {"unavailable": "libkriging_b200/host/_build/lkgpu_host_driver not built"}
-        except Exception as ex:  # pragma: no cover
-            fit_cpp = {"failed": str(ex)[:300]}
+                st.wait(["lkgpu/bench/cpp_fit_done"], timedelta(seconds=3000))
+            barrier()
 
     # ---- batched-occupancy path (BASELINE configs[4] shape) ----
     batched = None

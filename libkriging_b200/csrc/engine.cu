@@ -94,6 +94,25 @@ CUtensorMap make_map(double* base, long long rows, long long cols, long long ld,
   return m;
 }
 
+// 3D map of the same matrix for M-major operand tiles: dim0 = row inside a 16-row group (contiguous), dim1 = column
+// (k), dim2 = group of 16 rows (stride 128 B).  A box {16, 16, G} lands in shared memory as [group][k][16 rows] =
+// exactly G consecutive boxes {16 rows, 16 columns} of the 2D map, so one instruction per operand and stage replaces
+// 8 (N side, G = 8) or 4 (M side, G = 4); the 128-byte swizzle is a function of the shared-memory address alone and
+// stays what the fragment loads expect.  ok = false when the driver rejects the descriptor (the 2D path is used).
+CUtensorMap make_map3(double* base, long long rows, long long cols, long long ld, int groups, bool* ok) {
+  CUtensorMap m;
+  memset(&m, 0, sizeof(m));
+  cuuint64_t gdim[3] = {16, (cuuint64_t)cols, (cuuint64_t)(rows / 16)};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 8, 128};
+  cuuint32_t box[3] = {16, 16, (cuuint32_t)groups};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  *ok = (r == CUDA_SUCCESS);
+  return m;
+}
+
 // The tensor maps of one matrix live in DEVICE memory, one allocation per matrix that is written once and never
 // modified; kernels receive pointers to them (two 8-byte kernel parameters instead of two 128-byte __grid_constant__
 // descriptors, and the same descriptors serve every launch of the handle).
@@ -102,6 +121,8 @@ struct MatMaps {
   const CUtensorMap* km = nullptr;  // K-major operand tiles: box {16 k-rows, 64 columns}
   const CUtensorMap* wf = nullptr;  // wavefront sweep, forward: box {128 rows, 32 columns}, dense
   const CUtensorMap* wb = nullptr;  // wavefront sweep, backward: box {16 rows, 128 columns}, SWIZZLE_128B
+  const CUtensorMap* mm8 = nullptr;  // M-major operand tiles, 3D: box {16 rows, 16 k-columns, 8 row groups} (N side)
+  const CUtensorMap* mm4 = nullptr;  // the same with 4 row groups (M side); both null when the driver rejects them
 };
 
 // FP64 peak probe kernels ---------------------------------------------------
@@ -210,6 +231,7 @@ struct Engine {
   int persistent_update_reserve = 0;
   bool l2_order = true;  // LKGPU_NO_L2_ORDER=1: tile tables sorted by k-length only (the r01c order)
   int wave_grid_cap = 0;  // LKGPU_WAVE_GRID=k: at most k CTAs per sweep (fault localisation)
+  bool no_mm3 = false;  // LKGPU_NO_MM3=1: M-major operands as 2D boxes (12 TMA instructions per NT stage instead of 2)
   bool no_persistent = false;  // LKGPU_NO_PERSISTENT=1: one CTA per tile everywhere (fault localisation)
   bool ladder_shortcut = true;  // lkgpu_set_ladder_shortcut / LKGPU_FULL_LADDER=1 (see Engine::eval)
   bool use_abort = true;  // LKGPU_NO_ABORT=1: failed Cholesky attempts run to the end (fault localisation)
@@ -250,6 +272,14 @@ struct Engine {
   double *dRstar = nullptr, *dbeta = nullptr;
   TileDesc *trtri_tables = nullptr, *lauum_table = nullptr;
   int lauum_tiles = 0;
+  // Cholesky trailing updates in L2 order (build_chol_plans): one look-ahead + one rest table per outer block
+  TileDesc* chol_tables = nullptr;
+  struct CholPlan {
+    size_t off_la = 0, n_la = 0, off_rest = 0, n_rest = 0;
+  };
+  std::vector<CholPlan> chol_plans;  // indexed by J0 / chol_plan_OB
+  int chol_plan_OB = 0;
+  int chol_band = 32;  // 64-row tiles per band of the rest update (LKGPU_CHOL_BAND; 0: closed-form column order)
   struct TrtriLevel {
     size_t off1, n1, off2, n2;
   };
@@ -304,6 +334,9 @@ struct Engine {
     ladder_D = ladder_logdet = nullptr;
     if (trtri_tables) cudaFree(trtri_tables);
     if (lauum_table) cudaFree(lauum_table);
+    if (chol_tables) cudaFree(chol_tables);
+    chol_tables = nullptr;
+    chol_plans.clear();
     if (loo_table) cudaFree(loo_table);
     if (hpin) cudaFreeHost(hpin);
     for (CUtensorMap* m : map_allocs) cudaFree(m);
@@ -377,6 +410,8 @@ struct Engine {
     if (const char* v = getenv("LKGPU_PERSISTENT_UPDATE")) persistent_update_reserve = std::max(0, atoi(v));
     if (const char* v = getenv("LKGPU_OVERLAP_MAX_N")) overlap_max_n = std::max(0, atoi(v));
     if (const char* nlo = getenv("LKGPU_NO_L2_ORDER")) l2_order = !(nlo[0] == '1');
+    if (const char* v = getenv("LKGPU_CHOL_BAND")) chol_band = std::max(0, atoi(v));
+    if (const char* v = getenv("LKGPU_NO_MM3")) no_mm3 = v[0] == '1';
     const char* npe = getenv("LKGPU_NO_PERSISTENT");
     no_persistent = npe && npe[0] == '1';
     const char* nab = getenv("LKGPU_NO_ABORT");
@@ -408,7 +443,16 @@ struct Engine {
 
   std::vector<CUtensorMap*> map_allocs;  // device copies of the tensor maps (freed with the sized buffers)
   MatMaps maps_of(double* buf, bool with_sweep_maps) {
-    CUtensorMap h[4];
+    CUtensorMap h[6];
+    bool ok8 = false, ok4 = false;
+    h[4] = make_map3(buf, N, N, ld, 8, &ok8);
+    h[5] = make_map3(buf, N, N, ld, 4, &ok4);
+    const bool use3 = ok8 && ok4 && !no_mm3;
+    if (!(ok8 && ok4)) {
+      static bool warned = false;
+      if (!warned) fprintf(stderr, "[lkgpu] 3D tensor maps rejected by the driver; M-major operands use 2D boxes\n");
+      warned = true;
+    }
     h[0] = make_map(buf, N, N, ld, 16, 16);
     h[1] = make_map(buf, N, N, ld, 16, 64);
     if (with_sweep_maps) {
@@ -419,10 +463,10 @@ struct Engine {
       h[3] = h[0];
     }
     CUtensorMap* dm = nullptr;
-    CUDA_CHECK(cudaMalloc(&dm, 4 * sizeof(CUtensorMap)));
+    CUDA_CHECK(cudaMalloc(&dm, 6 * sizeof(CUtensorMap)));
     map_allocs.push_back(dm);
-    CUDA_CHECK(cudaMemcpy(dm, h, 4 * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-    return MatMaps{dm + 0, dm + 1, dm + 2, dm + 3};
+    CUDA_CHECK(cudaMemcpy(dm, h, 6 * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    return MatMaps{dm + 0, dm + 1, dm + 2, dm + 3, use3 ? dm + 4 : nullptr, use3 ? dm + 5 : nullptr};
   }
 
   // device workspaces, tensor maps and tile plans for the current n (a1: KModel)
@@ -729,6 +773,62 @@ struct Engine {
     lauum_tiles = (int)lt.size();
     lauum_table = dalloc<TileDesc>(lt.size());
     CUDA_CHECK(cudaMemcpy(lauum_table, lt.data(), lt.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
+    build_chol_plans();
+  }
+
+  // ---- Cholesky trailing updates: tile tables in L2 order ----
+  // The closed-form trapezoid order (SCHED_TRAP) walks one 128-column strip of C at a time: its N-side operand strip
+  // is shared by consecutive CTAs, but every column streams ALL M-side strips of the panel again, with a reuse
+  // distance of the whole panel (123 MB for the first k = 768 update at n = 20000) -- ncu: L2 hit rate 64 % = exactly
+  // the N-side share of the operand bytes, 6.5 GB of DRAM reads per launch, and 13 % of the warp time in the TRYWAIT
+  // on the ring's full barrier (profiles/r02b_ncu_syrk.csv, gpurun_out/r02c3/prof_syrk.ncu-rep source page).
+  // Here the rest update runs in horizontal bands of `chol_band` 64-row tiles, column by column inside a band: the
+  // band's M-side strips (chol_band x 393 KB) stay in L2 for the whole band and every N-side strip is read once per
+  // band by CTAs that run together; the look-ahead update (OB columns, all rows) runs row by row, its OB N-side
+  // strips resident.  Pure reordering: every tile computes what it computed before, bit for bit.
+  void build_chol_plans() {
+    chol_plans.clear();
+    chol_plan_OB = outer_panels > 0 ? outer_panels : (nb >= 96 ? 6 : 4);
+    if (chol_band <= 0 || !l2_order) return;
+    const int OB = chol_plan_OB;
+    std::vector<TileDesc> all;
+    for (int J0 = 0; J0 < nb; J0 += OB) {
+      CholPlan pl;
+      const int J1 = std::min(nb, J0 + OB);
+      const int rem = nb - J1;
+      const int c0 = J0 * BLK, c1 = J1 * BLK;
+      if (rem > OB) {
+        // look-ahead: region origin c1, 2 rem row tiles, OB column tiles, tm >= 2 tn; row-major
+        pl.off_la = all.size();
+        for (int tm = 0; tm < 2 * rem; ++tm)
+          for (int tn = 0; tn < OB && 2 * tn <= tm; ++tn) all.push_back({c1 + tm * TM, c1 + tn * TN, c0, c1});
+        pl.n_la = all.size() - pl.off_la;
+        // rest: region origin c1 + OB * BLK, 2 (rem - OB) row tiles, rem - OB column tiles; bands of rows
+        const int r0 = c1 + OB * BLK, mt = 2 * (rem - OB), nt = rem - OB;
+        pl.off_rest = all.size();
+        for (int b0 = 0; b0 < mt; b0 += chol_band) {
+          const int b1 = std::min(mt, b0 + chol_band);
+          for (int tn = 0; tn < nt && 2 * tn < b1; ++tn)
+            for (int tm = std::max(b0, 2 * tn); tm < b1; ++tm) all.push_back({r0 + tm * TM, r0 + tn * TN, c0, c1});
+        }
+        pl.n_rest = all.size() - pl.off_rest;
+      }
+      chol_plans.push_back(pl);
+    }
+    chol_tables = dalloc<TileDesc>(all.size());
+    if (!all.empty())
+      CUDA_CHECK(cudaMemcpy(chol_tables, all.data(), all.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
+  }
+  GemmArgs chol_table_args(size_t off, size_t count) {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.C = A;
+    a.ldc = ld;
+    a.sched = SCHED_TABLE;
+    a.epilogue = EPI_SUB;
+    a.table = chol_tables + off;
+    a.ntiles = (int)count;
+    return a;
   }
 
   // ---- GEMM launcher ----
@@ -748,10 +848,12 @@ struct Engine {
     }
     int grid = (persistent && !no_persistent) ? std::min(args.ntiles, 2 * sm_count) : args.ntiles;
     if (grid_cap > 0) grid = std::min(grid, grid_cap);
+    args.mm3 = (mM.mm4 != nullptr && mN.mm8 != nullptr) ? 1 : 0;
     if (layout == 0)
-      gemm_dmma_kernel<false, false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mM.mm, mN.mm, args);
+      gemm_dmma_kernel<false, false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(args.mm3 ? mM.mm4 : mM.mm,
+                                                                                  args.mm3 ? mN.mm8 : mN.mm, args);
     else if (layout == 1)
-      gemm_dmma_kernel<false, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mM.mm, mN.km, args);
+      gemm_dmma_kernel<false, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(args.mm3 ? mM.mm4 : mM.mm, mN.km, args);
     else
       gemm_dmma_kernel<true, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(mM.km, mN.km, args);
     CUDA_CHECK(cudaGetLastError());
@@ -835,6 +937,7 @@ struct Engine {
     dev_zero_ints(dinfo, 4);
     // measured at n = 20000 (nb = 157): 3 panels 97.9 ms, 4: 95.3, 5: 94.3, 6: 93.9, 8: 93.8; mid-size matrices keep 4
     const int OB = outer_panels > 0 ? outer_panels : (nb >= 96 ? 6 : 4);
+    const bool planned = Jstart == 0 && OB == chol_plan_OB && !chol_plans.empty() && persistent_update_reserve == 0;
     int last_upd = -1;
     for (int J0 = Jstart; J0 < nb; J0 += OB) {
       const int J1 = std::min(nb, J0 + OB);
@@ -857,7 +960,9 @@ struct Engine {
         CUDA_CHECK(cudaEventRecord(ev_panel[J0], s_main));
         if (last_upd >= 0) CUDA_CHECK(cudaStreamWaitEvent(s_main, ev_upd[last_upd], 0));
         // look-ahead: the next outer block's columns first, on the factorisation stream ...
-        gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1, 2 * rem, OB, c0, c1)), s_main, false);
+        const CholPlan* pl = planned ? &chol_plans[J0 / OB] : nullptr;
+        if (pl) gemm(0, mapA, A, mapA, A, chol_gemm(chol_table_args(pl->off_la, pl->n_la)), s_main, false);
+        else gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1, 2 * rem, OB, c0, c1)), s_main, false);
         // ... the rest of the trailing matrix on the low-priority stream
         CUDA_CHECK(cudaStreamWaitEvent(s_upd, ev_panel[J0], 0));
         // (experiment for round 2, off by default: LKGPU_PERSISTENT_UPDATE=r runs this update as a persistent grid on
@@ -865,6 +970,8 @@ struct Engine {
         if (persistent_update_reserve > 0)
           gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1 + OB * BLK, 2 * (rem - OB), rem - OB, c0, c1)), s_upd, true,
                2 * std::max(1, sm_count - persistent_update_reserve));
+        else if (pl)
+          gemm(0, mapA, A, mapA, A, chol_gemm(chol_table_args(pl->off_rest, pl->n_rest)), s_upd, false);
         else
           gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1 + OB * BLK, 2 * (rem - OB), rem - OB, c0, c1)), s_upd, false);
         CUDA_CHECK(cudaEventRecord(ev_upd[J0], s_upd));

@@ -2,7 +2,7 @@
 // update (SYRK), the panel TRSM, TRTRI and LAUUM.
 //
 // One persistent kernel, four warps per CTA, two CTAs per SM (96 KB smem each):
-//   * thread 0 is the TMA producer, inline in warp 0's loop: it issues the cp.async.bulk.tensor.2d
+//   * warp 0 is the TMA producer, inline in its consumer loop: one elected lane issues the cp.async.bulk.tensor
 //     (SWIZZLE_128B) loads of the two operand tiles of k-stage c+3 just before the CTA consumes k-stage c,
 //     into a 4-deep shared-memory ring guarded by full/empty mbarriers, running ahead across tile boundaries.
 //     (A producer-only fifth warp would put three warps on one SM sub-partition and cap every thread at
@@ -68,6 +68,8 @@ struct GemmArgs {
   const int* abort_flag;
   // Always 0; only read by the LKGPU_RING_RELEASE=0 build (round 1's never-taken fence, kept for A/B timing).
   int sched_fence;
+  // 1: M-major operands are described by 3D tensor maps (one box of 16 k x 64 / 128 rows per stage and operand)
+  int mm3;
 };
 
 __device__ __forceinline__ TileDesc gemm_get_tile(const GemmArgs& a, int id) {
@@ -174,7 +176,7 @@ gemm_dmma_kernel(const CUtensorMap* tmapM, const CUtensorMap* tmapN, const GemmA
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + GSTAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + GSTAGES;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
   // Abort flag: one read per CTA (so that the whole CTA takes the same branch even if the flag is raised right
   // now), issued before the barrier initialisation so that its latency hides behind it.
@@ -192,19 +194,27 @@ gemm_dmma_kernel(const CUtensorMap* tmapM, const CUtensorMap* tmapN, const GemmA
   __syncthreads();
   if (s_abort != 0) return;
 
-  // ===================== TMA producer: thread 0, inline in consumer warp 0 =====================
+  // ===================== TMA producer: warp 0, inline in its consumer loop =====================
   // Four warps per CTA and two CTAs per SM = two warps per SM sub-partition, so each thread may hold the
   // 64 accumulators + double-buffered fragments without spilling (a fifth, producer-only warp would put three
-  // warps on one sub-partition and cap everyone at 168 registers).  Thread 0 issues the loads of k-stage
+  // warps on one sub-partition and cap everyone at 168 registers).  Warp 0 issues the loads of k-stage
   // c + GSTAGES - 1 just before the CTA consumes k-stage c, i.e. it refills the slot released one iteration ago.
-  const bool is_producer = threadIdx.x == 0;
+  // All 32 lanes run the producer's bookkeeping on warp-uniform values and one elected lane issues the TMA
+  // instructions: ptxas keeps the operands in uniform registers (round 1-2a issued from `threadIdx.x == 0`, which
+  // made every UTMALDG a divergent-operand loop -- ELECT / 4 x R2UR / UTMALDG / BRA.U.ANY -- and with 12 boxes per
+  // stage in the NT layout warp 0 spent 21 % of a stage in the producer, the other warps waiting on the full barrier
+  // behind it: profiles/r02c_syrk_producer.md).  M-major operands come as ONE 3D box per operand (args.mm3, see
+  // MatMaps) instead of 8 + 4 two-dimensional ones.
+  const bool is_producer = warp == 0;
   int p_tile = blockIdx.x, p_k0 = 0, p_stage = 0;
   uint32_t p_phase = 0;
   bool p_live = false;
   TileDesc p_td = {0, 0, 0, 0};
   if (is_producer) {
-    tma_prefetch_desc(tmapM);
-    tma_prefetch_desc(tmapN);
+    if (elect_one()) {
+      tma_prefetch_desc(tmapM);
+      tma_prefetch_desc(tmapN);
+    }
     p_live = p_tile < args.ntiles;
     if (p_live) {
       p_td = gemm_get_tile(args, p_tile);
@@ -214,21 +224,27 @@ gemm_dmma_kernel(const CUtensorMap* tmapM, const CUtensorMap* tmapN, const GemmA
   auto produce_one = [&]() {
     if (!p_live) return;
     mbar_wait(&empty_bar[p_stage], p_phase ^ 1);
-    uint8_t* sN = ring + p_stage * STAGE_BYTES;
-    uint8_t* sM = sN + NS_TILE_BYTES;
-    mbar_arrive_expect_tx(&full_bar[p_stage], STAGE_BYTES);
-    if (NS_KMAJ) {
+    if (elect_one()) {
+      uint8_t* sN = ring + p_stage * STAGE_BYTES;
+      uint8_t* sM = sN + NS_TILE_BYTES;
+      mbar_arrive_expect_tx(&full_bar[p_stage], STAGE_BYTES);
+      if (NS_KMAJ) {
 #pragma unroll
-      for (int b = 0; b < TN / 64; ++b) tma_load_2d(sN + b * 8192, tmapN, &full_bar[p_stage], p_k0, p_td.c_col + 64 * b);
-    } else {
+        for (int b = 0; b < TN / 64; ++b) tma_load_2d(sN + b * 8192, tmapN, &full_bar[p_stage], p_k0, p_td.c_col + 64 * b);
+      } else if (args.mm3) {
+        tma_load_3d(sN, tmapN, &full_bar[p_stage], 0, p_k0, p_td.c_col >> 4);
+      } else {
 #pragma unroll
-      for (int b = 0; b < TN / 16; ++b) tma_load_2d(sN + b * 2048, tmapN, &full_bar[p_stage], p_td.c_col + 16 * b, p_k0);
-    }
-    if (MS_KMAJ) {
-      tma_load_2d(sM, tmapM, &full_bar[p_stage], p_k0, p_td.c_row);
-    } else {
+        for (int b = 0; b < TN / 16; ++b) tma_load_2d(sN + b * 2048, tmapN, &full_bar[p_stage], p_td.c_col + 16 * b, p_k0);
+      }
+      if (MS_KMAJ) {
+        tma_load_2d(sM, tmapM, &full_bar[p_stage], p_k0, p_td.c_row);
+      } else if (args.mm3) {
+        tma_load_3d(sM, tmapM, &full_bar[p_stage], 0, p_k0, p_td.c_row >> 4);
+      } else {
 #pragma unroll
-      for (int b = 0; b < TM / 16; ++b) tma_load_2d(sM + b * 2048, tmapM, &full_bar[p_stage], p_td.c_row + 16 * b, p_k0);
+        for (int b = 0; b < TM / 16; ++b) tma_load_2d(sM + b * 2048, tmapM, &full_bar[p_stage], p_td.c_row + 16 * b, p_k0);
+      }
     }
     if (++p_stage == GSTAGES) {
       p_stage = 0;

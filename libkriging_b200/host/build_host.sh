@@ -21,12 +21,14 @@ INC="-I$DEPS/armadillo-code/include -I$DEPS/lbfgsb_cpp/include -I$HERE/../../inc
 pids=()
 g++ $CXXFLAGS $INC -c "$HERE/lkgpu_kriging.cpp" -o "$OUT/obj/lkgpu_kriging.o" & pids+=($!)
 g++ $CXXFLAGS $INC -c "$HERE/lkgpu_host_driver.cpp" -o "$OUT/obj/lkgpu_host_driver.o" & pids+=($!)
+g++ $CXXFLAGS -c "$HERE/lkgpu_comm.cpp" -o "$OUT/obj/lkgpu_comm.o" & pids+=($!)
 for f in blas lbfgsb linpack s_cmp s_copy timer; do
   gcc -O2 -fPIC -w -I"$DEPS/lbfgsb_cpp/Lbfgsb.3.0" -I"$DEPS/lbfgsb_cpp/Lbfgsb.3.0/include" \
       -c "$DEPS/lbfgsb_cpp/Lbfgsb.3.0/$f.c" -o "$OUT/obj/lb_$f.o" & pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-g++ -shared -o "$OUT/liblkgpu_host.so" "$OUT/obj/lkgpu_kriging.o" "$OUT"/obj/lb_*.o -L"$HERE/.." -llkgpu -Wl,-rpath,'$ORIGIN/../..'
+g++ -shared -o "$OUT/liblkgpu_host.so" "$OUT/obj/lkgpu_kriging.o" "$OUT/obj/lkgpu_comm.o" "$OUT"/obj/lb_*.o -L"$HERE/.." -llkgpu -Wl,-rpath,'$ORIGIN/../..'
 g++ -o "$OUT/lkgpu_host_driver" "$OUT/obj/lkgpu_host_driver.o" -L"$OUT" -llkgpu_host -L"$HERE/.." -llkgpu \
     -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../..' -lpthread
+g++ -O2 -std=c++17 -o "$OUT/lkgpu_comm_selftest" "$HERE/lkgpu_comm_selftest.cpp" "$HERE/lkgpu_comm.cpp" -lpthread
 echo "[build_host] built $OUT/lkgpu_host_driver"

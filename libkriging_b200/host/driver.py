@@ -26,9 +26,13 @@ def build() -> bool:
 
 def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL", regmodel="constant", normalize=False,
         mode="eval", optim="none", theta=None, gamma=None, grad=True, sigma2=None, est_sigma2=None, nugget=None,
-        est_nugget=None, Xn=None, device=0, timeout=None, update=None, concurrent_starts=None, beta=None):
+        est_nugget=None, Xn=None, device=0, timeout=None, update=None, concurrent_starts=None, beta=None,
+        world=1, devices=None, env=None):
     """Run lkgpu::Kriging on (X, y): mode='fit' (optim=BFGS[#]) or 'eval' (objective value / gradient at theta or
-    gamma).  Returns the driver's JSON (theta, beta, sigma2, nugget, objective_at_fit, pred_mean, pred_sd, ...)."""
+    gamma).  Returns the driver's JSON (theta, beta, sigma2, nugget, objective_at_fit, pred_mean, pred_sd, ...).
+    world > 1: a sharded fit -- `world` driver processes (one per entry of `devices`, default device r for rank r; the
+    same device may be named twice) share the multistart rows over lkgpu::ShardComm; returns the list of their JSONs
+    in rank order."""
     if not available():
         raise RuntimeError(f"{DRIVER} is missing: run libkriging_b200/host/build_host.sh in the build container")
     X = np.asfortranarray(X, dtype=np.float64)
@@ -73,11 +77,44 @@ def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL",
         with open(os.path.join(wd, "cfg.txt"), "w") as f:
             for k, v in cfg.items():
                 f.write(f"{k}={v}\n")
-        out = subprocess.run([DRIVER, wd], capture_output=True, text=True, timeout=timeout)
-        lines = out.stdout.strip().splitlines()
-        if not lines:
-            raise RuntimeError(f"lkgpu_host_driver produced no output (rc={out.returncode}): {out.stderr[-1000:]}")
-        res = json.loads(lines[-1])
-        if "error" in res:
-            raise RuntimeError(res["error"])
-        return res
+        if world <= 1:
+            penv = dict(os.environ, **(env or {}))
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):  # a single process, even under torchrun
+                penv.pop(k, None)
+            out = subprocess.run([DRIVER, wd], capture_output=True, text=True, timeout=timeout, env=penv)
+            return _parse(out.stdout, out.stderr, out.returncode)
+        devices = list(devices) if devices is not None else list(range(world))
+        port = _free_port()
+        procs = []
+        for r in range(world):
+            penv = dict(os.environ, **(env or {}))
+            penv.update(RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                        MASTER_PORT=str(port), LKGPU_COMM_PORT_OFFSET="0", LKGPU_HOST_DEVICE=str(devices[r]))
+            procs.append(subprocess.Popen([DRIVER, wd], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=penv))
+        outs = []
+        try:
+            for pr in procs:
+                so, se = pr.communicate(timeout=timeout)
+                outs.append((so, se, pr.returncode))
+        finally:
+            for pr in procs:
+                if pr.poll() is None:
+                    pr.kill()
+        return [_parse(*o) for o in outs]
+
+
+def _free_port() -> int:
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _parse(stdout, stderr, rc):
+    lines = stdout.strip().splitlines()
+    if not lines:
+        raise RuntimeError(f"lkgpu_host_driver produced no output (rc={rc}): {stderr[-1000:]}")
+    res = json.loads(lines[-1])
+    if "error" in res:
+        raise RuntimeError(res["error"])
+    return res

@@ -1,6 +1,9 @@
 // lkgpu_host_driver.cpp -- command-line front end of the C++ host (lkgpu::Kriging), same work-directory protocol
 // and JSON output as oracle/ref_driver.cpp so that the tests can put the two side by side:
 //   <workdir>/cfg.txt (key=value), X.bin (n*d column-major), y.bin, noise.bin, theta.bin (nt*d), gamma.bin, Xn.bin (m*d)
+// Sharded fit: launched once per GPU with RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT in the environment
+// (LOCAL_RANK or LKGPU_HOST_DEVICE picks the device) the processes share the multistart rows over lkgpu::ShardComm;
+// every process prints its own JSON line (same model on all of them, plus its rank and the starts it ran).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +12,7 @@
 #include <map>
 #include <sstream>
 
+#include "lkgpu_comm.hpp"
 #include "lkgpu_kriging.hpp"
 
 static std::vector<double> read_bin(const std::string& path, size_t count) {
@@ -50,8 +54,14 @@ int main(int argc, char** argv) {
   const std::string mode = gets("mode", "eval"), kernel = gets("kernel", "gauss"), noise_model = gets("noise_model", "none");
   const std::string objective = gets("objective", "LL"), regmodel = gets("regmodel", "constant"), optim = gets("optim", "none");
   const bool normalize = geti("normalize", 0) != 0;
-  const int nt = geti("ntheta", 1), want_grad = geti("grad", 1), device = geti("device", 0);
+  const int nt = geti("ntheta", 1), want_grad = geti("grad", 1);
+  int device = geti("device", 0);
   try {
+    std::unique_ptr<lkgpu::ShardComm> comm = lkgpu::ShardComm::from_env();
+    if (comm) {
+      if (const char* dv = getenv("LKGPU_HOST_DEVICE")) device = atoi(dv);
+      else if (const char* lr = getenv("LOCAL_RANK")) device = atoi(lr);
+    }
     arma::mat X(read_bin(wd + "/X.bin", (size_t)n * d).data(), n, d);
     arma::vec y(read_bin(wd + "/y.bin", n).data(), n);
     arma::vec noise;
@@ -60,6 +70,7 @@ int main(int argc, char** argv) {
     const NM nm = noise_model == "nugget" ? NM::Nugget : noise_model == "hetero" ? NM::Heterogeneous : NM::None;
     lkgpu::Kriging k(kernel, nm, device);
     if (cfg.count("concurrent_starts")) k.set_concurrent_starts(geti("concurrent_starts", 0));
+    if (comm) k.set_comm(comm.get());
     lkgpu::Kriging::Parameters prm;
     if (geti("beta_n", 0) > 0) {  // fixed trend coefficients (Parameters::beta, is_beta_estim = false)
       const int bn = geti("beta_n", 0);
@@ -76,6 +87,12 @@ int main(int argc, char** argv) {
     else k.fit(y, X, regmodel, normalize, mode == "fit" ? optim : "none", objective, prm);
     js << "\"fit_s\": " << (now_s() - t0) << ", \"n_eval\": " << k.n_eval() << ", \"concurrent_starts\": "
        << k.last_concurrency() << ", ";
+    if (comm) {
+      js << "\"rank\": " << comm->rank() << ", \"world\": " << comm->world() << ", \"device\": " << device
+         << ", \"local_n_eval\": " << k.local_n_eval() << ", \"local_starts\": [";
+      for (size_t i = 0; i < k.local_starts().size(); ++i) js << (i ? ", " : "") << k.local_starts()[i];
+      js << "], ";
+    }
     if (mode == "eval") {
       const int gd = d + (nm == NM::None ? 0 : 1);
       arma::vec gamma = exists(wd + "/gamma.bin") ? arma::vec(read_bin(wd + "/gamma.bin", gd).data(), gd)
@@ -122,6 +139,7 @@ int main(int argc, char** argv) {
     }
     js << "\"n\": " << n << ", \"d\": " << d << "}";
     std::cout << js.str() << std::endl;
+    if (comm) comm->barrier();  // leave together (rank 0 serves the others until they are done)
   } catch (const std::exception& e) {
     std::cout << "{\"error\": \"" << e.what() << "\"}" << std::endl;
     return 1;

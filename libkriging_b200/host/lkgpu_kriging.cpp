@@ -3,6 +3,7 @@
 // lbfgsb::Optimizer run per start with the restart rule, argmin with the strict '<' tie rule, and the commit
 // formulas.  The objective itself (populate_Model + reductions) is one lkgpu_objective_fun call.
 #include "lkgpu_kriging.hpp"
+#include "lkgpu_comm.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -33,6 +34,11 @@ constexpr double NUGGET_ALPHA_LOWER = 1e-3;  // Kriging.cpp:678
 // they are inside lbfgsb::Optimizer::minimize and drop it only for the duration of an objective evaluation -- the
 // part that runs on the GPU and is worth overlapping.
 std::mutex g_lbfgsb_mutex;
+std::atomic<long long> g_fit_seq{0};  // key of a sharded fit's start queue (lkgpu_comm.hpp)
+bool env_is_one(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] == '1';
+}
 
 void check(int rc) {
   if (rc != 0) throw std::runtime_error(lkgpu_last_error());
@@ -157,6 +163,12 @@ double Kriging::objective_on(void* h, int obj, const arma::vec& gamma, arma::vec
 // Number of engine handles with overlapping evaluations for this process's multistart rows (the batched-occupancy
 // path of BASELINE cfg 5): a factorisation of n <= 8192 cannot fill 148 SMs, so such fits keep several starts in
 // flight, one handle and one host thread each.  set_concurrent_starts(K) overrides; results do not depend on it.
+void Kriging::set_comm(ShardComm* comm) {
+  m_comm = comm;
+  m_rank = comm ? comm->rank() : 0;
+  m_world = comm ? comm->world() : 1;
+}
+
 int Kriging::concurrency(int n_starts, arma::uword n) const {
   int want = m_concurrent_starts > 0 ? m_concurrent_starts : (n <= 3072 ? 8 : (n <= 8192 ? 4 : 1));
   want = std::max(1, std::min(want, n_starts));
@@ -471,15 +483,37 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
     return res;
   };
 
-  // this process's starts: {s : s mod world == rank}, several of them in flight when n is mid-size
+  // this process's starts, several of them in flight when n is mid-size: static {s : s mod world ==
+  // rank}, or -- sharded fit with more starts than processes -- drawn from the shared ticket counter
+  const bool dynamic = m_comm != nullptr && (int)multistart > m_world && !env_is_one("LKGPU_STATIC_STARTS");
   std::vector<arma::uword> mine;
-  for (arma::uword s = 0; s < multistart; ++s)
-    if ((int)(s % (arma::uword)m_world) == m_rank) mine.push_back(s);
-  const int ncon = concurrency((int)mine.size(), n);
+  if (!dynamic)
+    for (arma::uword s = 0; s < multistart; ++s)
+      if ((int)(s % (arma::uword)m_world) == m_rank) mine.push_back(s);
+  const long long queue_key = ++g_fit_seq;  // every process runs the same sequence of fits
+  std::atomic<size_t> next_static{0};
+  auto next_start = [&]() -> long long {
+    if (dynamic) {
+      const long long t = m_comm->next_ticket(queue_key);
+      return t < (long long)multistart ? t : -1;
+    }
+    const size_t k = next_static.fetch_add(1);
+    return k < mine.size() ? (long long)mine[k] : -1;
+  };
+  const int share = dynamic ? (int)((multistart + m_world - 1) / m_world) : (int)mine.size();
+  const int ncon = concurrency(share, n);
   m_last_concurrency = ncon;
-  std::vector<StartResult> results(mine.size());
+  std::vector<StartResult> results;
+  std::mutex results_mutex;
+  auto run_starts = [&](void* h) {
+    for (long long s = next_start(); s >= 0; s = next_start()) {
+      StartResult r = optimize_worker((arma::uword)s, h);
+      std::lock_guard<std::mutex> lk(results_mutex);
+      results.push_back(std::move(r));
+    }
+  };
   if (ncon <= 1) {
-    for (size_t k = 0; k < mine.size(); ++k) results[k] = optimize_worker(mine[k], m_h);
+    run_starts(m_h);
   } else {
     // one engine handle (own workspaces, own CUDA streams) and one host thread per start in flight
     std::vector<void*> handles{m_h};
@@ -491,13 +525,8 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
         handles.push_back(h);
         check(lkgpu_set_params(h, m_est_sigma2, m_sigma2, m_est_nugget, m_nugget, m_alpha));
       }
-      std::atomic<size_t> next{0};
       std::vector<std::thread> pool;
-      for (int w = 0; w < ncon; ++w)
-        pool.emplace_back([&, w]() {
-          for (size_t k = next.fetch_add(1); k < mine.size(); k = next.fetch_add(1))
-            results[k] = optimize_worker(mine[k], handles[w]);
-        });
+      for (int w = 0; w < ncon; ++w) pool.emplace_back([&, w]() { run_starts(handles[w]); });
       for (auto& t : pool) t.join();
     } catch (...) {
       for (size_t w = 1; w < handles.size(); ++w) lkgpu_destroy(handles[w]);
@@ -505,13 +534,53 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
     }
     for (size_t w = 1; w < handles.size(); ++w) lkgpu_destroy(handles[w]);
   }
+  std::sort(results.begin(), results.end(),
+            [](const StartResult& a, const StartResult& b) { return a.start_index < b.start_index; });
+  m_local_n_eval = 0;
+  m_local_starts.clear();
+  for (const StartResult& r : results) {
+    m_local_n_eval += r.n_eval;
+    m_local_starts.push_back(r.start_index);
+  }
+  if (m_comm != nullptr) {
+    // one all-gather of a row per start: [start, success, objective, n_eval, retries, gamma]; afterwards every
+    // process holds every start's result (the owner's bits) in start order
+    const size_t width = 5 + gd;
+    std::vector<double> rows;
+    for (const StartResult& r : results) {
+      rows.push_back((double)r.start_index);
+      rows.push_back(r.success ? 1.0 : 0.0);
+      rows.push_back(r.objective_value);
+      rows.push_back((double)r.n_eval);
+      rows.push_back((double)r.retries);
+      for (arma::uword q = 0; q < gd; ++q) rows.push_back(r.success ? r.gamma[q] : 0.0);
+    }
+    const std::vector<double> all = m_comm->allgather(rows);
+    if (all.size() != width * multistart)
+      throw std::runtime_error("sharded fit: " + std::to_string(all.size() / width) + " start results gathered, " +
+                               std::to_string(multistart) + " expected");
+    results.assign(multistart, StartResult());
+    for (size_t k = 0; k < multistart; ++k) {
+      const double* row = all.data() + k * width;
+      StartResult r;
+      r.start_index = (int)row[0];
+      r.success = row[1] > 0.5;
+      r.objective_value = row[2];
+      r.n_eval = (int)row[3];
+      r.retries = (int)row[4];
+      r.gamma = arma::vec(row + 5, gd);
+      if (r.start_index < 0 || r.start_index >= (int)multistart || results[r.start_index].start_index >= 0)
+        throw std::runtime_error("sharded fit: start results do not cover the starts exactly once");
+      results[r.start_index] = r;
+    }
+  }
   for (const StartResult& r : results) {
     m_n_eval += r.n_eval;
     m_results.push_back(r);
   }
   m_have_scalars = false;
 
-  if (m_world > 1) return;  // the caller exchanges start_results() and calls commit(gamma*)
+  if (m_world > 1 && m_comm == nullptr) return;  // set_shard: the caller exchanges start_results() and calls commit(gamma*)
   // ---- argmin over successful starts, strict '<' in start order (Kriging.cpp:2097-2114) ----
   int best = -1;
   double min_ofn = std::numeric_limits<double>::infinity();

@@ -16,6 +16,8 @@
 
 namespace lkgpu {
 
+class ShardComm;  // lkgpu_comm.hpp
+
 struct OptimConfig {  // Optim:: statics of the reference (src/lib/Optim.cpp:39-141)
   bool reparametrize = true;
   double theta_lower_factor = 0.02, theta_upper_factor = 10.0;
@@ -57,6 +59,13 @@ class Kriging {
   // multistart sharding: this process runs the starts {s : s mod world == rank}; the caller
   // exchanges start_results() (16 B per start) and calls commit(gamma*) on every rank.
   void set_shard(int rank, int world) { m_rank = rank; m_world = world; }
+  // Sharded fit with the exchange done here (lkgpu_comm.hpp: one process per GPU, TCP star around rank 0): with more
+  // starts than processes the start indices come from a shared ticket counter (dynamic queue), otherwise process r
+  // takes {s : s mod world == r}; after the starts every process holds ALL start_results(), applies the reference's
+  // argmin and commits the same model.  `comm` must outlive the fit calls.
+  void set_comm(ShardComm* comm);
+  int local_n_eval() const { return m_local_n_eval; }           // evaluations this process ran in the last fit
+  const std::vector<int>& local_starts() const { return m_local_starts; }  // start indices this process ran
   // Multistart rows in flight on this process's GPU (0 = by size: 8 for n <= 3072, 4 for n <= 8192, else 1).  One
   // engine handle and one host thread per row in flight; the L-BFGS-B code itself (not thread-safe: f2c statics)
   // runs under a process-wide mutex that is released for the duration of every objective evaluation.
@@ -115,6 +124,9 @@ class Kriging {
   std::string m_kernel, m_objective = "LL", m_regmodel = "constant";
   NoiseModel m_noise_model;
   int m_device, m_rank = 0, m_world = 1, m_concurrent_starts = 0, m_last_concurrency = 1;
+  ShardComm* m_comm = nullptr;
+  int m_local_n_eval = 0;
+  std::vector<int> m_local_starts;
   void* m_h = nullptr;
   bool m_is_empty = true, m_normalize = false;
   bool m_est_beta = true, m_est_sigma2 = true, m_est_nugget = true, m_est_theta = true, m_used_block = false;

@@ -140,3 +140,25 @@ def test_cpp_host_fixed_beta_matches_reference():
         assert relerr_vec(r["beta"], c["beta_out"]) < 1e-14
         assert relerr_vec(r["pred_mean"], c["pred_mean"]) < tol, c["name"]
         assert relerr_vec(r["pred_sd"], c["pred_sd"]) < tol * 10, c["name"]
+
+
+@pytest.mark.gpu
+def test_cpp_host_sharded_fit_equals_single_process(monkeypatch):
+    """The C++ host's sharded fit (lkgpu::ShardComm, one process per rank; here two processes on ONE device so that the
+    test runs on a single-GPU box): BFGS6 with the dynamic start queue and with the static s mod G assignment return
+    the single-process model bit for bit on every rank, and the ranks' start lists partition 0..5.  (Plain ladder, as
+    in the concurrent-workers test: which handle a start runs on changes the shortcut's history.)"""
+    X, y, _ = synth(700, 3, 17, "smooth")
+    monkeypatch.setenv("LKGPU_FULL_LADDER", "1")
+    one = host.run(X, y, kernel="matern5_2", mode="fit", optim="BFGS6", concurrent_starts=1)
+    for env in ({}, {"LKGPU_STATIC_STARTS": "1"}):
+        rs = host.run(X, y, kernel="matern5_2", mode="fit", optim="BFGS6", concurrent_starts=2, world=2, devices=[0, 0],
+                      env=env, timeout=600)
+        assert [r["rank"] for r in rs] == [0, 1] and all(r["world"] == 2 for r in rs)
+        assert sorted(rs[0]["local_starts"] + rs[1]["local_starts"]) == list(range(6))
+        if env:
+            assert rs[0]["local_starts"] == [0, 2, 4] and rs[1]["local_starts"] == [1, 3, 5]
+        for r in rs:
+            assert r["theta"] == one["theta"] and r["sigma2"] == one["sigma2"] and r["beta"] == one["beta"]
+            assert r["objective_at_fit"] == one["objective_at_fit"] and r["n_eval"] == one["n_eval"]
+        assert rs[0]["local_n_eval"] + rs[1]["local_n_eval"] == one["n_eval"]
