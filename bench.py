@@ -642,14 +642,16 @@ def run_b200_arm(args, cfg):
                     fit_cpp = {"host": "libkriging_b200/host/lkgpu_host_driver (C++: Armadillo + lbfgsb_cpp)",
                                "processes": world, "optim": "BFGS" if world == 1 else optim,
                                "wall_s": max(float(q["fit_s"]) for q in rs),
+                               "cuda_init_s": max(float(q.get("cuda_init_s", 0.0)) for q in rs),
                                "wall_s_incl_process_start": time.perf_counter() - t0,
                                "n_eval": int(r["n_eval"]), "LL_at_fit": float(r["objective_at_fit"]),
                                "theta": [float(t) for t in r["theta"]], "sigma2": float(r["sigma2"])}
                     if world > 1:
                         fit_cpp["exchange"] = ("lkgpu::ShardComm: tickets for the start queue + one all-gather of a row per "
                                                "start over TCP (rank 0 serves); no GPU traffic")
-                        fit_cpp["per_rank"] = [{"rank": q["rank"], "device": q["device"], "fit_s": float(q["fit_s"]),
-                                                "evals": int(q["local_n_eval"]), "starts": q["local_starts"]} for q in rs]
+                        fit_cpp["per_rank"] = [{"rank": q["rank"], "device": q["rank"], "fit_s": float(q["fit_s"]),
+                                                "cuda_init_s": q.get("cuda_init_s"), "evals": int(q["local_n_eval"]),
+                                                "starts": q["local_starts"]} for q in rs]
                         fit_cpp["all_ranks_same_model"] = all(q["theta"] == r["theta"] and q["sigma2"] == r["sigma2"]
                                                               for q in rs)
                     th_py = np.asarray(fit["theta"])

@@ -86,10 +86,14 @@ def run(X, y, *, kernel="gauss", noise_model="none", noise=None, objective="LL",
         devices = list(devices) if devices is not None else list(range(world))
         port = _free_port()
         procs = []
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        visible = [v for v in visible.split(",") if v] if visible else None
         for r in range(world):
             penv = dict(os.environ, **(env or {}))
+            # each process sees its own GPU only (the driver initialises one device instead of all of them)
             penv.update(RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
-                        MASTER_PORT=str(port), LKGPU_COMM_PORT_OFFSET="0", LKGPU_HOST_DEVICE=str(devices[r]))
+                        MASTER_PORT=str(port), LKGPU_COMM_PORT_OFFSET="0", LKGPU_HOST_DEVICE="0",
+                        CUDA_VISIBLE_DEVICES=visible[devices[r]] if visible else str(devices[r]))
             procs.append(subprocess.Popen([DRIVER, wd], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=penv))
         outs = []
         try:

@@ -12,6 +12,7 @@
 #include <map>
 #include <sstream>
 
+#include "../../include/lkgpu.h"
 #include "lkgpu_comm.hpp"
 #include "lkgpu_kriging.hpp"
 
@@ -82,6 +83,14 @@ int main(int argc, char** argv) {
     if (cfg.count("nugget")) { prm.nugget = getd("nugget", 0.0); prm.is_nugget_estim = geti("est_nugget", 0) != 0; }
     std::ostringstream js;
     js << "{";
+    // CUDA start-up of this process (driver initialisation + context on `device`) is not part of the fit: timed apart
+    {
+      const double tc = now_s();
+      unsigned long long free_b = 0, total_b = 0;
+      lkgpu_mem_info(device, &free_b, &total_b);
+      js << "\"cuda_init_s\": " << (now_s() - tc) << ", ";
+    }
+    if (comm) comm->barrier();  // sharded fit: the processes start their fits together
     const double t0 = now_s();
     if (nm == NM::Heterogeneous) k.fit(y, noise, X, regmodel, normalize, mode == "fit" ? optim : "none", objective, prm);
     else k.fit(y, X, regmodel, normalize, mode == "fit" ? optim : "none", objective, prm);

@@ -132,9 +132,15 @@ class LbfgsbResult:
 def lbfgsb_minimize(func, x0, lb, ub, *, m=10, max_iter=20, max_fun=15000, factr=1e10, pgtol=1e-3, maxls=20):
     """Minimise func(x) -> (f, g) within [lb, ub] (nbd = 2 everywhere).  x0 is not modified; returns the
     final x.  Termination mirrors lbfgsb_cpp: stop at NEW_X once isave[29] >= max_iter."""
+    import scipy
     from scipy.optimize import _lbfgsb
     from scipy.optimize._lbfgsb_py import status_messages
 
+    # private SciPy API: the C translation of L-BFGS-B 3.0 with integer task codes and the ln_task argument came with
+    # SciPy 1.15 (this image has it); older releases take a different setulb signature -- fail loudly, not strangely
+    if tuple(int(p) for p in scipy.__version__.split(".")[:2]) < (1, 15):
+        raise RuntimeError(f"libkriging_b200 needs SciPy >= 1.15 for its L-BFGS-B loop (found {scipy.__version__}); "
+                           "the C++ host (libkriging_b200/host) has no such dependency")
     try:
         from scipy.optimize._lbfgsb_py import HAS_ILP64
     except ImportError:  # pragma: no cover

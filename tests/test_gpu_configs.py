@@ -148,3 +148,38 @@ def test_sigma2_variogram_with_duplicates(capi):
     with capi.Engine(X, y, np.ones((100, 1)), kernel="gauss", noise_model="hetero", noise=np.full(100, 0.1)) as e:
         s = e.sigma2_variogram()
     assert relerr(s, ko.sigma2_variogram(X, y)) < 1e-12
+
+
+def test_cfg1_fit_matches_reference_fit():
+    """BASELINE config 1, the reference's own bench shape (bench/bench-kriging.cpp: Kriging('gauss') fit, BFGS, LL,
+    n = 1000, d = 4, y = sum sin(2 pi x_k)), against a FIT of the unmodified reference (tests/golden/refgen_cfg1_fit.json,
+    generator make_golden_cfg1.py), through both hosts.  The fit ends at theta ~ 6 with sigma2 = 1.4e7: numerically
+    singular matrices, the jitter ladder active on most evaluations -- the oracle backend on the CPU reproduces the
+    reference's theta to 7e-6 and its LL to 3e-7 there (tests/test_host_fit.py), so the device gates are the ones of
+    the default-start fits (tests/test_gpu_fit.py); the evaluation AT the reference's theta is gated tighter."""
+    import json
+    import os
+    from libkriging_b200.host import driver as host
+    from libkriging_b200.kriging import Kriging
+    from tests.golden.make_golden_cfg1 import synth_cfg1
+    from tests.util import GOLDEN
+    c = json.load(open(os.path.join(GOLDEN, "refgen_cfg1_fit.json")))
+    X, y = synth_cfg1()
+    assert relerr(float(np.sum(y)), c["y_sum"]) < 1e-12
+    Xn = np.random.Generator(np.random.PCG64(1123)).random((20, 4))
+    k = Kriging("gauss")
+    k.fit(y, X, "constant", False, "BFGS", "LL")
+    assert relerr(k.logLikelihood(), c["objective_at_fit"]) < 1e-5
+    assert relerr(k.theta(), c["theta"]) < 5e-3
+    assert relerr(k.sigma2(), c["sigma2"]) < 5e-2
+    mean, sd = k.predict(Xn, True)
+    assert relerr_vec(mean, c["pred_mean"]) < 5e-3
+    # the objective at the reference's own fitted theta (a jitter-ladder point)
+    v, g = k.logLikelihoodFun(np.asarray(c["theta"]), True)
+    assert relerr(v, c["value_at_theta_fit"]) < 1e-6
+    k.close()
+    if host.available():
+        r = host.run(X, y, kernel="gauss", mode="fit", optim="BFGS", Xn=Xn)
+        assert relerr(r["objective_at_fit"], c["objective_at_fit"]) < 1e-5
+        assert relerr(r["theta"], c["theta"]) < 5e-3
+        assert relerr(r["sigma2"], c["sigma2"]) < 5e-2
