@@ -412,6 +412,8 @@ struct Engine {
     if (const char* nlo = getenv("LKGPU_NO_L2_ORDER")) l2_order = !(nlo[0] == '1');
     if (const char* v = getenv("LKGPU_CHOL_BAND")) chol_band = std::max(0, atoi(v));
     if (const char* v = getenv("LKGPU_NO_MM3")) no_mm3 = v[0] == '1';
+    if (const char* v = getenv("LKGPU_TRACE_CHOL")) trace_chol = v[0] == '1';
+    if (const char* v = getenv("LKGPU_UPDATE_AFTER_LOOKAHEAD")) update_after_lookahead = v[0] != '0' ? 1 : 0;
     const char* npe = getenv("LKGPU_NO_PERSISTENT");
     no_persistent = npe && npe[0] == '1';
     const char* nab = getenv("LKGPU_NO_ABORT");
@@ -933,8 +935,34 @@ struct Engine {
   }
   // Jstart > 0: the panels < Jstart already hold L (kept factor + row-block solve) and the trailing block
   // [Jstart.., Jstart..] holds the Schur complement: chol_block's last step (LinearAlgebra.cpp:286).
+  // LKGPU_TRACE_CHOL=1 (diagnostics): timing events after every launch of the factorisation stream; the intervals
+  // (completion to completion, so launch gaps and dependency waits are inside them) go to stderr after the stage.
+  bool trace_chol = false;
+  // 1: the rest update starts after the look-ahead update, 0: beside it, -1: by size (after it for nb < 96: n = 5000
+  // chol 4.46 -> 4.31 ms; beside it above: n = 20000 83.9 against 84.9 ms).  LKGPU_UPDATE_AFTER_LOOKAHEAD overrides.
+  int update_after_lookahead = -1;
+  std::vector<std::pair<cudaEvent_t, std::string>> trace_marks;
+  void trace_mark(const char* what, int j) {
+    if (!trace_chol) return;
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    CUDA_CHECK(cudaEventRecord(e, s_main));
+    trace_marks.push_back({e, std::string(what) + " " + std::to_string(j)});
+  }
+  void trace_dump() {
+    if (!trace_chol || trace_marks.empty()) return;
+    CUDA_CHECK(cudaStreamSynchronize(s_main));
+    for (size_t i = 1; i < trace_marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, trace_marks[i - 1].first, trace_marks[i].first);
+      fprintf(stderr, "[trace] %-14s %9.2f us\n", trace_marks[i].second.c_str(), 1e3 * ms);
+    }
+    for (auto& m : trace_marks) cudaEventDestroy(m.first);
+    trace_marks.clear();
+  }
   void cholesky(int Jstart = 0) {
     dev_zero_ints(dinfo, 4);
+    trace_mark("start", Jstart);
     // measured at n = 20000 (nb = 157): 3 panels 97.9 ms, 4: 95.3, 5: 94.3, 6: 93.9, 8: 93.8; mid-size matrices keep 4
     const int OB = outer_panels > 0 ? outer_panels : (nb >= 96 ? 6 : 4);
     const bool planned = Jstart == 0 && OB == chol_plan_OB && !chol_plans.empty() && persistent_update_reserve == 0;
@@ -947,12 +975,15 @@ struct Engine {
         ++launches;
         potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM_BYTES, s_main>>>(A, W, ld, jb, logdet_blocks, j, dinfo, use_abort ? 1 : 0);
         CUDA_CHECK(cudaGetLastError());
+        trace_mark("potf2", j);
         const int rem = nb - j - 1;
         if (rem == 0) break;
         // panel TRSM as GEMM with the inverted diagonal block: A[i, j] <- A[i, j] * Dinv_j^T  (in place)
         gemm(0, mapA, A, mapW, W, chol_gemm(rect_args(A, EPI_SET, jb + BLK, jb, 2 * rem, 1, jb, jb + BLK)), s_main, false);
+        trace_mark("trsm", j);
         const int ncol = J1 - (j + 1);  // panels of this outer block still to be factored
         if (ncol > 0) gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(jb + BLK, 2 * rem, ncol, jb, jb + BLK)), s_main, false);
+        if (ncol > 0) trace_mark("inblock", j);
       }
       const int rem = nb - J1;  // panels after this outer block
       if (rem <= 0) break;
@@ -963,7 +994,13 @@ struct Engine {
         const CholPlan* pl = planned ? &chol_plans[J0 / OB] : nullptr;
         if (pl) gemm(0, mapA, A, mapA, A, chol_gemm(chol_table_args(pl->off_la, pl->n_la)), s_main, false);
         else gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1, 2 * rem, OB, c0, c1)), s_main, false);
-        // ... the rest of the trailing matrix on the low-priority stream
+        trace_mark("lookahead", J0);
+        // ... the rest of the trailing matrix on the low-priority stream.  Mid-size matrices start it when the look-ahead
+        // update has finished, together with the next block's first panel kernel: that kernel needs a whole SM (231 KB of
+        // shared memory), and if the rest update -- started beside the look-ahead update -- already fills the machine, it
+        // waits for an SM to drain (LKGPU_TRACE_CHOL: 127 instead of 59 us at n = 5000, once per outer block).
+        if (update_after_lookahead > 0 || (update_after_lookahead < 0 && nb < 96))
+          CUDA_CHECK(cudaEventRecord(ev_panel[J0], s_main));
         CUDA_CHECK(cudaStreamWaitEvent(s_upd, ev_panel[J0], 0));
         // (experiment for round 2, off by default: LKGPU_PERSISTENT_UPDATE=r runs this update as a persistent grid on
         //  2 (SMs - r) CTAs -- the run-ahead producer then hides each tile's prologue -- leaving r SMs to the panel chain)
@@ -982,9 +1019,11 @@ struct Engine {
           last_upd = -1;
         }
         gemm(0, mapA, A, mapA, A, chol_gemm(trap_args(c1, 2 * rem, rem, c0, c1)), s_main, false);
+        trace_mark("update", J0);
       }
     }
     if (last_upd >= 0) CUDA_CHECK(cudaStreamWaitEvent(s_main, ev_upd[last_upd], 0));
+    trace_dump();
   }
 
   // ---- block extension of the kept factor (f3) ----------------------------------------------------------------
