@@ -279,6 +279,13 @@ struct Engine {
   };
   std::vector<CholPlan> chol_plans;  // indexed by J0 / chol_plan_OB
   int chol_plan_OB = 0;
+  // LKGPU_LAUUM_ORDER: 0 super-tiles (order_for_l2), 1 rows (longest k first) in serpentine rounds, 2 rows, 3 bands of
+  // LKGPU_LAUUM_BAND row tiles in serpentine rounds.  n = 20000, DRAM reads / L2 hit rate / time of the launch: 0: 121 GB,
+  // 51 %, 77.07 ms; 1: 101 GB, 56 %, 76.88; 2: 148 GB, 45 %, 77.30; 3 with bands of 4 / 8 / 16 / 32: 90 / 67 / 57 / 75 GB,
+  // 60 / 69 / 70 / 64 %, 76.60 / 76.61 / 76.58 / 76.67 ms (profiles/r02c_table_orders.log)
+  int lauum_order = 3;
+  int lauum_band = 16;
+  int trtri_order = 1;  // LKGPU_TRTRI_ORDER: 0 longest k first, 1 + serpentine rounds
   int chol_band = 32;  // 64-row tiles per band of the rest update (LKGPU_CHOL_BAND; 0: closed-form column order)
   struct TrtriLevel {
     size_t off1, n1, off2, n2;
@@ -411,6 +418,9 @@ struct Engine {
     if (const char* v = getenv("LKGPU_OVERLAP_MAX_N")) overlap_max_n = std::max(0, atoi(v));
     if (const char* nlo = getenv("LKGPU_NO_L2_ORDER")) l2_order = !(nlo[0] == '1');
     if (const char* v = getenv("LKGPU_CHOL_BAND")) chol_band = std::max(0, atoi(v));
+    if (const char* v = getenv("LKGPU_LAUUM_ORDER")) lauum_order = atoi(v);
+    if (const char* v = getenv("LKGPU_TRTRI_ORDER")) trtri_order = atoi(v);
+    if (const char* v = getenv("LKGPU_LAUUM_BAND")) lauum_band = std::max(1, atoi(v));
     if (const char* v = getenv("LKGPU_NO_MM3")) no_mm3 = v[0] == '1';
     if (const char* v = getenv("LKGPU_TRACE_CHOL")) trace_chol = v[0] == '1';
     if (const char* v = getenv("LKGPU_UPDATE_AFTER_LOOKAHEAD")) update_after_lookahead = v[0] != '0' ? 1 : 0;
@@ -718,6 +728,15 @@ struct Engine {
     for (const Group& g : groups) t.insert(t.end(), g.tiles.begin(), g.tiles.end());
   }
 
+  // A persistent grid of G CTAs walks a table in rounds (CTA b takes tiles b, b + G, ...).  In a table sorted by k-length
+  // CTA 0 would get the longest tile of EVERY round and CTA G - 1 the shortest: the CTAs drift apart by the length spread
+  // of a round per round, and tiles that share an operand strip (neighbours in the table, started together) stop
+  // meeting in L2.  Reversing every other round cancels the drift over two rounds.  Pure reordering.
+  void serpentine(std::vector<TileDesc>& t) const {
+    const size_t G = (size_t)2 * sm_count;
+    for (size_t c0 = G; c0 < t.size(); c0 += 2 * G) std::reverse(t.begin() + c0, t.begin() + std::min(t.size(), c0 + G));
+  }
+
   // ---- TRTRI (recursive, level-batched) and LAUUM tile tables ----
   void build_plans() {
     struct Node {
@@ -756,6 +775,13 @@ struct Engine {
       auto by_len = [](const TileDesc& x, const TileDesc& y) { return (x.k_end - x.k_begin) > (y.k_end - y.k_begin); };
       std::stable_sort(t1.begin(), t1.end(), by_len);
       std::stable_sort(t2.begin(), t2.end(), by_len);
+      // serpentine rounds: TRTRI 77.0 -> 75.6 ms at n = 20000, DRAM reads of the top level 28 + 49 -> 19 + 23 GB.  (Blocks of
+      // 4 columns x 74 rows / 8 rows x 37 columns in serpentine rounds, the LAUUM recipe, were slower here: 76.7 ms --
+      // the block edges do not line up with the rounds; profiles/r02c_table_orders.log)
+      if (trtri_order == 1) {
+        serpentine(t1);
+        serpentine(t2);
+      }
       TrtriLevel lv;
       lv.off1 = all.size();
       lv.n1 = t1.size();
@@ -771,7 +797,22 @@ struct Engine {
     std::vector<TileDesc> lt;
     for (int rt = 0; rt < 2 * nb; ++rt)
       for (int ct = 0; 2 * ct <= rt; ++ct) lt.push_back({rt * TM, ct * TN, rt * TM, N});
-    if (l2_order) order_for_l2(lt);
+    if (lauum_order == 0) {
+      if (l2_order) order_for_l2(lt);
+    } else if (lauum_order == 1) {
+      serpentine(lt);  // (rows in ascending order = longest k first already)
+    } else if (lauum_order == 3) {
+      // bands of lauum_band row tiles (k ranges within lauum_band * 64 of each other), column by column inside a band:
+      // a round of 2 * SMs consecutive tiles is a block of lauum_band rows x ~(2 * SMs / lauum_band) columns whose
+      // tiles start together and walk k together -- every N-side strip is shared by lauum_band tiles, every M-side
+      // strip by the round's columns; serpentine rounds keep the CTAs in step
+      lt.clear();
+      for (int b0 = 0; b0 < 2 * nb; b0 += lauum_band)
+        for (int ct = 0; 2 * ct < std::min(2 * nb, b0 + lauum_band); ++ct)
+          for (int rt = std::max(b0, 2 * ct); rt < std::min(2 * nb, b0 + lauum_band); ++rt)
+            lt.push_back({rt * TM, ct * TN, rt * TM, N});
+      serpentine(lt);
+    }
     lauum_tiles = (int)lt.size();
     lauum_table = dalloc<TileDesc>(lt.size());
     CUDA_CHECK(cudaMemcpy(lauum_table, lt.data(), lt.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));

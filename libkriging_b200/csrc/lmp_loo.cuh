@@ -344,10 +344,19 @@ void Engine::loo_finish(int want_grad) {
   CUDA_CHECK(cudaGetLastError());
   {
     if (!loo_table) {
+      // every tile walks the whole k range: rounds of the persistent grid are blocks of lauum_band rows x
+      // ~(2 SMs / lauum_band) columns that start together and stay together (see build_plans, LAUUM order 3)
       std::vector<TileDesc> lt;
-      for (int rt = 0; rt < 2 * nb; ++rt)
-        for (int ct = 0; 2 * ct <= rt; ++ct) lt.push_back({rt * TM, ct * TN, 0, N});
-      if (l2_order) order_for_l2(lt);
+      if (lauum_order == 3) {
+        for (int b0 = 0; b0 < 2 * nb; b0 += lauum_band)
+          for (int ct = 0; 2 * ct < std::min(2 * nb, b0 + lauum_band); ++ct)
+            for (int rt = std::max(b0, 2 * ct); rt < std::min(2 * nb, b0 + lauum_band); ++rt)
+              lt.push_back({rt * TM, ct * TN, 0, N});
+      } else {
+        for (int rt = 0; rt < 2 * nb; ++rt)
+          for (int ct = 0; 2 * ct <= rt; ++ct) lt.push_back({rt * TM, ct * TN, 0, N});
+        if (l2_order) order_for_l2(lt);
+      }
       loo_tiles = (int)lt.size();
       loo_table = dalloc<TileDesc>(lt.size());
       CUDA_CHECK(cudaMemcpy(loo_table, lt.data(), lt.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));

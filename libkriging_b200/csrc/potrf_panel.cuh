@@ -237,9 +237,11 @@ potf2_inv_kernel(double* __restrict__ A, double* __restrict__ W, long long ld, i
   } else {
     for (int idx = tid; idx < 128 * 64; idx += POTF2_THREADS - 32) {
       const int c = idx >> 6, r2 = (idx & 63) * 2;
-      double2 v = *reinterpret_cast<const double2*>(As + c * 128 + r2);
+      // pairs that lie wholly above the diagonal are not read: the upper blocks of As become the inverse stage's T
+      // scratch as soon as the first warp gets there (racecheck: read here against the write of T below)
+      double2 v = make_double2(0.0, 0.0);
+      if (r2 + 1 >= c) v = *reinterpret_cast<const double2*>(As + c * 128 + r2);
       if (r2 < c) v.x = 0.0;
-      if (r2 + 1 < c) v.y = 0.0;
       *reinterpret_cast<double2*>(Ablk + (long long)c * ld + r2) = v;
     }
   }
