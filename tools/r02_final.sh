@@ -16,6 +16,8 @@ echo "== ncu full captures"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_dmma -s 353 -c 1 -f -o $O/prof_lauum python tools/profile_eval.py 20000 10 1 > $O/ncu_lauum.log 2>&1; tail -1 $O/ncu_lauum.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_dmma -s 12 -c 1 -f -o $O/prof_syrk python tools/profile_eval.py 20000 10 1 > $O/ncu_syrk.log 2>&1; tail -1 $O/ncu_syrk.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_dmma -s 351 -c 2 -f -o $O/prof_trtri python tools/profile_eval.py 20000 10 1 > $O/ncu_trtri.log 2>&1; tail -1 $O/ncu_trtri.log
+echo "== two overlapping n = 20000 handles"; timeout 600 python tools/bench_concurrent.py 20000 10 matern5_2 3 1,2 2>&1 | tail -2 | tee $O/concurrent_n20000.log
+echo "== 1..16 overlapping n = 5000 handles"; timeout 600 python tools/bench_concurrent.py 5000 20 gauss 10 1,2,4,8,16 2>&1 | tail -5 | tee $O/concurrent_n5000.log
 echo "== compute-sanitizer (overlapping evaluations, n = 1500)"
 timeout 600 compute-sanitizer --tool racecheck python tools/diag_concurrent2.py 1500 3 2 > $O/racecheck.log 2>&1; tail -3 $O/racecheck.log
 timeout 600 compute-sanitizer --tool memcheck python tools/diag_concurrent2.py 1500 3 2 > $O/memcheck.log 2>&1; tail -3 $O/memcheck.log
