@@ -479,6 +479,7 @@ def run_b200_arm(args, cfg):
     dev = torch.device("cuda", local)
     from libkriging_b200 import _capi
     from libkriging_b200.kriging import Kriging
+    import scipy.optimize._lbfgsb_py  # noqa: F401  (the Python host's L-BFGS-B: its ~1 s import is not part of a fit)
     comm = None
     if world > 1:
         from libkriging_b200 import parallel
