@@ -95,15 +95,20 @@ def test_model_members(capi, kernel, n, d):
     with capi.Engine(X, y, F, kernel=kernel) as e:
         r = e.eval_raw("LL", theta, want_grad=True)
         assert r["n_jitter"] == m.n_jitter
-        assert relerr(r["SSEstar"], m.SSEstar) < 1e-9
+        # Gates scaled by the conditioning of R (two backward-stable factorisations agree to ~ cond(R) eps):
+        # tol = 2 cond(R) eps = 1.4e-10 / 6.2e-10 / 1e-13 (floor) / 2.2e-11 for the four cases.  Measured on a B200
+        # (tools/probe_members.py): Rinv 2.6e-12 / 1.5e-11 / 1.3e-15 / 6.8e-13, Estar 1.1e-12 / 8.2e-12 / 6.6e-15 /
+        # 1.6e-13, L <= 8.8e-14, SSEstar <= 4.9e-12 -- all within north_star's 1e-10.
+        tol = max(1e-13, 2.0 * np.linalg.cond(m.R) * np.finfo(float).eps)
+        assert relerr(r["SSEstar"], m.SSEstar) < tol
         assert relerr(r["sum_log_diagL"], np.sum(np.log(np.diag(m.L)))) < 1e-12
-        assert relerr_vec(r["betahat"], m.betahat) < 1e-9
+        assert relerr_vec(r["betahat"], m.betahat) < tol
         assert relerr_vec(e.export("R"), m.R) < 1e-14
-        assert relerr_vec(e.export("L"), m.L) < 1e-10
-        assert relerr_vec(e.export("Rinv"), m.Rinv) < 1e-8
-        assert relerr_vec(e.export("Fstar"), m.Fstar) < 1e-9
-        assert relerr_vec(e.export("ystar"), m.ystar) < 1e-9
-        assert relerr_vec(e.export("Estar"), m.Estar) < 1e-7
+        assert relerr_vec(e.export("L"), m.L) < tol
+        assert relerr_vec(e.export("Rinv"), m.Rinv) < tol
+        assert relerr_vec(e.export("Fstar"), m.Fstar) < tol
+        assert relerr_vec(e.export("ystar"), m.ystar) < tol
+        assert relerr_vec(e.export("Estar"), m.Estar) < tol
         assert relerr_vec(np.abs(e.export("Rstar")), np.abs(m.Rstar)) < 1e-9
         L = e.export("L")
         assert np.all(np.triu(L, 1) == 0.0)
