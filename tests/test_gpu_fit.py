@@ -38,9 +38,12 @@ def test_gpu_fit_matches_reference(c):
     if c["objective"] == "LOO":
         assert obj <= c["objective_at_fit"] * (1 + 1e-3)  # minimised; value ~ 4e-8, flat in theta
     else:
+        # measured on a B200 (profiles/r02c_fit_deviations.log): objective <= 2.4e-9, theta <= 1.3e-6 (the m52-n200-d3
+        # fixture, whose start is the numerically singular one; all others <= 2.9e-7), sigma2 <= 7.4e-7.  Round 1 gated
+        # theta at 5e-3 and sigma2 at 5e-2.
         assert relerr(obj, c["objective_at_fit"]) < 1e-6
-        assert relerr(k.theta(), c["theta"]) < 5e-3
-        assert relerr(k.sigma2(), c["sigma2"]) < 5e-2
+        assert relerr(k.theta(), c["theta"]) < 2e-5
+        assert relerr(k.sigma2(), c["sigma2"]) < 1e-4
     k.close()
 
 
