@@ -57,9 +57,11 @@ def test_cpp_host_fit_default_starts(c):
     if c["objective"] == "LOO":
         assert r["objective_at_fit"] <= c["objective_at_fit"] * (1 + 1e-3)
     else:
+        # measured (profiles/r02c_fit_deviations.log): objective <= 3.0e-9, theta <= 7.9e-5, sigma2 <= 8.2e-5 (the gauss
+        # fixture; the others <= 1.3e-6)
         assert relerr(r["objective_at_fit"], c["objective_at_fit"]) < 1e-6
-        assert relerr(r["theta"], c["theta"]) < 5e-3
-        assert relerr(r["sigma2"], c["sigma2"]) < 5e-2
+        assert relerr(r["theta"], c["theta"]) < 5e-4
+        assert relerr(r["sigma2"], c["sigma2"]) < 5e-4
 
 
 with open(os.path.join(GOLDEN, "refgen_updates.json")) as _f:

@@ -155,8 +155,8 @@ def test_cfg1_fit_matches_reference_fit():
     n = 1000, d = 4, y = sum sin(2 pi x_k)), against a FIT of the unmodified reference (tests/golden/refgen_cfg1_fit.json,
     generator make_golden_cfg1.py), through both hosts.  The fit ends at theta ~ 6 with sigma2 = 1.4e7: numerically
     singular matrices, the jitter ladder active on most evaluations -- the oracle backend on the CPU reproduces the
-    reference's theta to 7e-6 and its LL to 3e-7 there (tests/test_host_fit.py), so the device gates are the ones of
-    the default-start fits (tests/test_gpu_fit.py); the evaluation AT the reference's theta is gated tighter."""
+    reference's theta to 7e-6 and its LL to 3e-7 there (tests/test_host_fit.py); the gates below sit a few times above the
+    deviations measured on a B200."""
     import json
     import os
     from libkriging_b200.host import driver as host
@@ -169,17 +169,21 @@ def test_cfg1_fit_matches_reference_fit():
     Xn = np.random.Generator(np.random.PCG64(1123)).random((20, 4))
     k = Kriging("gauss")
     k.fit(y, X, "constant", False, "BFGS", "LL")
-    assert relerr(k.logLikelihood(), c["objective_at_fit"]) < 1e-5
-    assert relerr(k.theta(), c["theta"]) < 5e-3
-    assert relerr(k.sigma2(), c["sigma2"]) < 5e-2
+    # measured on a B200 (profiles/r02c_fit_deviations.log): LL 5.2e-7, theta 3.5e-4, sigma2 4.4e-5, predict mean 6.1e-6
+    # (SciPy's L-BFGS-B: its line search leaves the reference's trajectory on this flat, singular likelihood)
+    assert relerr(k.logLikelihood(), c["objective_at_fit"]) < 5e-6
+    assert relerr(k.theta(), c["theta"]) < 2e-3
+    assert relerr(k.sigma2(), c["sigma2"]) < 5e-4
     mean, sd = k.predict(Xn, True)
-    assert relerr_vec(mean, c["pred_mean"]) < 5e-3
-    # the objective at the reference's own fitted theta (a jitter-ladder point)
+    assert relerr_vec(mean, c["pred_mean"]) < 1e-4
+    # the objective at the reference's own fitted theta: a jitter-ladder point (R numerically singular, sigma2 = 1.4e7);
+    # measured 7.0e-7 -- the reference differs from itself by 1.4e-8 at such points
     v, g = k.logLikelihoodFun(np.asarray(c["theta"]), True)
-    assert relerr(v, c["value_at_theta_fit"]) < 1e-6
+    assert relerr(v, c["value_at_theta_fit"]) < 5e-6
     k.close()
     if host.available():
+        # the C++ host runs the reference's own lbfgsb_cpp: measured LL 8.9e-7, theta 7.0e-6, sigma2 1.1e-6
         r = host.run(X, y, kernel="gauss", mode="fit", optim="BFGS", Xn=Xn)
-        assert relerr(r["objective_at_fit"], c["objective_at_fit"]) < 1e-5
-        assert relerr(r["theta"], c["theta"]) < 5e-3
-        assert relerr(r["sigma2"], c["sigma2"]) < 5e-2
+        assert relerr(r["objective_at_fit"], c["objective_at_fit"]) < 5e-6
+        assert relerr(r["theta"], c["theta"]) < 1e-4
+        assert relerr(r["sigma2"], c["sigma2"]) < 1e-4
