@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblkgpu.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "cov.cuh", "gemm_dmma.cuh", "potrf_panel.cuh", "trsv.cuh", "trsv_wave.cuh", "variogram.cuh", "lmp_loo.cuh", "objective.inl",
+HEADERS = ["common.cuh", "tile_tables.hpp", "cov.cuh", "gemm_dmma.cuh", "potrf_panel.cuh", "trsv.cuh", "trsv_wave.cuh", "variogram.cuh", "lmp_loo.cuh", "objective.inl",
            os.path.join("..", "..", "include", "lkgpu.h")]
 
 

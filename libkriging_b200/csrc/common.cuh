@@ -4,9 +4,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "tile_tables.hpp"
+
 namespace lk {
 
-constexpr int BLK = 128;  // factorisation block size; every n*n buffer is padded to a multiple of it
+// BLK = 128, the factorisation block size (every n*n buffer is padded to a multiple of it), is defined in
+// tile_tables.hpp
 
 // ---------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA (cp.async.bulk.tensor), FP64 DMMA

@@ -728,14 +728,8 @@ struct Engine {
     for (const Group& g : groups) t.insert(t.end(), g.tiles.begin(), g.tiles.end());
   }
 
-  // A persistent grid of G CTAs walks a table in rounds (CTA b takes tiles b, b + G, ...).  In a table sorted by k-length
-  // CTA 0 would get the longest tile of EVERY round and CTA G - 1 the shortest: the CTAs drift apart by the length spread
-  // of a round per round, and tiles that share an operand strip (neighbours in the table, started together) stop
-  // meeting in L2.  Reversing every other round cancels the drift over two rounds.  Pure reordering.
-  void serpentine(std::vector<TileDesc>& t) const {
-    const size_t G = (size_t)2 * sm_count;
-    for (size_t c0 = G; c0 < t.size(); c0 += 2 * G) std::reverse(t.begin() + c0, t.begin() + std::min(t.size(), c0 + G));
-  }
+  // rounds of the persistent grid (2 CTAs per SM): see tables::serpentine
+  void serpentine(std::vector<TileDesc>& t) const { tables::serpentine(t, (size_t)2 * sm_count); }
 
   // ---- TRTRI (recursive, level-batched) and LAUUM tile tables ----
   void build_plans() {
@@ -794,9 +788,7 @@ struct Engine {
     trtri_tables = dalloc<TileDesc>(all.size());
     if (!all.empty())
       CUDA_CHECK(cudaMemcpy(trtri_tables, all.data(), all.size() * sizeof(TileDesc), cudaMemcpyHostToDevice));
-    std::vector<TileDesc> lt;
-    for (int rt = 0; rt < 2 * nb; ++rt)
-      for (int ct = 0; 2 * ct <= rt; ++ct) lt.push_back({rt * TM, ct * TN, rt * TM, N});
+    std::vector<TileDesc> lt = tables::lower_tiles_by_row(nb, N, true);
     if (lauum_order == 0) {
       if (l2_order) order_for_l2(lt);
     } else if (lauum_order == 1) {
@@ -806,11 +798,7 @@ struct Engine {
       // a round of 2 * SMs consecutive tiles is a block of lauum_band rows x ~(2 * SMs / lauum_band) columns whose
       // tiles start together and walk k together -- every N-side strip is shared by lauum_band tiles, every M-side
       // strip by the round's columns; serpentine rounds keep the CTAs in step
-      lt.clear();
-      for (int b0 = 0; b0 < 2 * nb; b0 += lauum_band)
-        for (int ct = 0; 2 * ct < std::min(2 * nb, b0 + lauum_band); ++ct)
-          for (int rt = std::max(b0, 2 * ct); rt < std::min(2 * nb, b0 + lauum_band); ++rt)
-            lt.push_back({rt * TM, ct * TN, rt * TM, N});
+      lt = tables::lower_tiles_in_bands(nb, N, lauum_band, true);
       serpentine(lt);
     }
     lauum_tiles = (int)lt.size();
@@ -843,17 +831,11 @@ struct Engine {
       if (rem > OB) {
         // look-ahead: region origin c1, 2 rem row tiles, OB column tiles, tm >= 2 tn; row-major
         pl.off_la = all.size();
-        for (int tm = 0; tm < 2 * rem; ++tm)
-          for (int tn = 0; tn < OB && 2 * tn <= tm; ++tn) all.push_back({c1 + tm * TM, c1 + tn * TN, c0, c1});
+        tables::chol_lookahead_tiles(all, c0, c1, rem, OB);
         pl.n_la = all.size() - pl.off_la;
         // rest: region origin c1 + OB * BLK, 2 (rem - OB) row tiles, rem - OB column tiles; bands of rows
-        const int r0 = c1 + OB * BLK, mt = 2 * (rem - OB), nt = rem - OB;
         pl.off_rest = all.size();
-        for (int b0 = 0; b0 < mt; b0 += chol_band) {
-          const int b1 = std::min(mt, b0 + chol_band);
-          for (int tn = 0; tn < nt && 2 * tn < b1; ++tn)
-            for (int tm = std::max(b0, 2 * tn); tm < b1; ++tm) all.push_back({r0 + tm * TM, r0 + tn * TN, c0, c1});
-        }
+        tables::chol_rest_tiles(all, c0, c1, c1 + OB * BLK, 2 * (rem - OB), rem - OB, chol_band);
         pl.n_rest = all.size() - pl.off_rest;
       }
       chol_plans.push_back(pl);

@@ -26,6 +26,7 @@
 //   lane (g = lane/4, t = lane%4): acc[i][j] = C[c_row + 8j + 2t (+1)][c_col + 8(4w+i) + g].
 #pragma once
 #include "common.cuh"
+#include "tile_tables.hpp"
 
 #ifndef LKGPU_RING_RELEASE
 #define LKGPU_RING_RELEASE 1  // 1: real per-lane proxy fence before the ring-slot release; 0: round 1's never-taken fence
@@ -33,8 +34,8 @@
 
 namespace lk {
 
-constexpr int TM = 64;       // C rows per tile
-constexpr int TN = 128;      // C cols per tile
+// TM = 64 (C rows per tile), TN = 128 (C cols per tile) and TileDesc live in tile_tables.hpp (plain C++, shared with
+// the CPU self-test of the table builders)
 constexpr int TK = 16;       // k per pipeline stage (16 doubles = one 128-byte swizzle row)
 constexpr int GSTAGES = 4;   // pipeline depth
 constexpr int GEMM_CONSUMER_WARPS = 4;
@@ -46,10 +47,6 @@ constexpr int GEMM_SMEM_BYTES = GSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 2
 
 enum GemmEpilogue { EPI_SET = 0, EPI_SETNEG = 1, EPI_SUB = 2 };
 enum GemmSched { SCHED_TABLE = 0, SCHED_RECT = 1, SCHED_TRAP = 2 };
-
-struct TileDesc {
-  int c_row, c_col, k_begin, k_end;
-};
 
 struct GemmArgs {
   double* C;          // output buffer (column-major)

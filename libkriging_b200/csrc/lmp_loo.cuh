@@ -348,13 +348,9 @@ void Engine::loo_finish(int want_grad) {
       // ~(2 SMs / lauum_band) columns that start together and stay together (see build_plans, LAUUM order 3)
       std::vector<TileDesc> lt;
       if (lauum_order == 3) {
-        for (int b0 = 0; b0 < 2 * nb; b0 += lauum_band)
-          for (int ct = 0; 2 * ct < std::min(2 * nb, b0 + lauum_band); ++ct)
-            for (int rt = std::max(b0, 2 * ct); rt < std::min(2 * nb, b0 + lauum_band); ++rt)
-              lt.push_back({rt * TM, ct * TN, 0, N});
+        lt = tables::lower_tiles_in_bands(nb, N, lauum_band, false);
       } else {
-        for (int rt = 0; rt < 2 * nb; ++rt)
-          for (int ct = 0; 2 * ct <= rt; ++ct) lt.push_back({rt * TM, ct * TN, 0, N});
+        lt = tables::lower_tiles_by_row(nb, N, false);
         if (l2_order) order_for_l2(lt);
       }
       loo_tiles = (int)lt.size();
