@@ -157,6 +157,7 @@ void ShardComm::serve() {
   std::vector<bool> have(m_world, false);
   std::vector<int> fd_of_rank(m_world, -1);
   int n_have = 0, n_closed = 0;
+  bool lost = false;  // a peer went away: no later all-gather can complete, the others must fail instead of waiting
   try {
     while (true) {
       std::vector<pollfd> pf;
@@ -181,6 +182,8 @@ void ShardComm::serve() {
           ::close(fds[i]);
           fds[i] = -1;
           ++n_closed;
+          lost = true;
+          if (n_have > 0) throw std::runtime_error("a process left during an all-gather");
           continue;
         }
         if (h.op == OP_HELLO) {
@@ -193,6 +196,7 @@ void ShardComm::serve() {
         } else if (h.op == OP_GATHER) {
           const int rk = rank_of[i];
           if (rk < 0 || have[rk]) throw std::runtime_error("unexpected GATHER");
+          if (lost) throw std::runtime_error("all-gather after a process left");
           parts[rk].resize((size_t)h.count);
           if (h.count > 0) read_all(fds[i], parts[rk].data(), (size_t)h.count * sizeof(double));
           have[rk] = true;
@@ -215,7 +219,8 @@ void ShardComm::serve() {
       }
     }
   } catch (const std::exception&) {
-    // a broken connection ends the server; the clients see their sockets close and raise
+    // a broken connection, or a process that left before the exchange was over (it failed: the normal exit is after the
+    // last barrier), ends the server; the clients see their sockets close and raise instead of waiting for ever
   }
   for (int fd : fds)
     if (fd >= 0) ::close(fd);

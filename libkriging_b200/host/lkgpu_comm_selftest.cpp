@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
+#include <exception>
 #include <thread>
 
 #include "lkgpu_comm.hpp"
@@ -12,19 +14,31 @@ int main() {
   try {
     auto comm = lkgpu::ShardComm::from_env();
     if (!comm) { printf("{\"error\": \"WORLD_SIZE <= 1\"}\n"); return 2; }
+    // failure injection (tests/test_host_comm.py): this rank leaves before the exchange; the others must fail, not hang
+    if (const char* die = getenv("LKGPU_COMM_SELFTEST_DIE"); die && atoi(die) == comm->rank()) {
+      printf("{\"rank\": %d, \"left_early\": true}\n", comm->rank());
+      return 3;
+    }
     const int total = 50;
     std::vector<double> taken;
     std::mutex mu;
     std::vector<std::thread> pool;
+    std::exception_ptr failure;
     for (int w = 0; w < 3; ++w)
       pool.emplace_back([&]() {
-        for (long long t = comm->next_ticket(7); t < total; t = comm->next_ticket(7)) {
+        try {
+          for (long long t = comm->next_ticket(7); t < total; t = comm->next_ticket(7)) {
+            std::lock_guard<std::mutex> lk(mu);
+            taken.push_back((double)t);
+            std::this_thread::sleep_for(std::chrono::milliseconds(1 + comm->rank()));
+          }
+        } catch (...) {
           std::lock_guard<std::mutex> lk(mu);
-          taken.push_back((double)t);
-          std::this_thread::sleep_for(std::chrono::milliseconds(1 + comm->rank()));
+          if (!failure) failure = std::current_exception();
         }
       });
     for (auto& t : pool) t.join();
+    if (failure) std::rethrow_exception(failure);
     std::vector<long long> counts;
     std::vector<double> all = comm->allgather(taken, &counts);
     std::sort(all.begin(), all.end());

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <limits>
 #include <mutex>
 #include <random>
@@ -526,8 +527,18 @@ void Kriging::fit_impl(const arma::vec& y, const arma::vec* noise, const arma::m
         check(lkgpu_set_params(h, m_est_sigma2, m_sigma2, m_est_nugget, m_nugget, m_alpha));
       }
       std::vector<std::thread> pool;
-      for (int w = 0; w < ncon; ++w) pool.emplace_back([&, w]() { run_starts(handles[w]); });
+      std::exception_ptr failure;  // e.g. the start queue's connection lost: rethrown on this thread after the join
+      for (int w = 0; w < ncon; ++w)
+        pool.emplace_back([&, w]() {
+          try {
+            run_starts(handles[w]);
+          } catch (...) {
+            std::lock_guard<std::mutex> lk(results_mutex);
+            if (!failure) failure = std::current_exception();
+          }
+        });
       for (auto& t : pool) t.join();
+      if (failure) std::rethrow_exception(failure);
     } catch (...) {
       for (size_t w = 1; w < handles.size(); ++w) lkgpu_destroy(handles[w]);
       throw;
