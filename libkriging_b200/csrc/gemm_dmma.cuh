@@ -6,7 +6,7 @@
 //     (SWIZZLE_128B) loads of the two operand tiles of k-stage c+3 just before the CTA consumes k-stage c,
 //     into a 4-deep shared-memory ring guarded by full/empty mbarriers, running ahead across tile boundaries.
 //     (A producer-only fifth warp would put three warps on one SM sub-partition and cap every thread at
-//     168 registers -- measured: spills in the main loop; with 2 warps per sub-partition the kernel uses ~210.)
+//     168 registers -- measured: spills in the main loop; with 2 warps per sub-partition the kernel uses 190 - 214.)
 //   * all four warps are consumers: each owns a 64(row) x 32(col) slab of the 64 x 128 output tile as 32
 //     independent m8n8k4 FP64 accumulators (DMMA.8x8x4), reads its fragments conflict-free from the swizzled
 //     tiles with register + immediate addressing, software-pipelined one k-step ahead, and applies the
@@ -39,7 +39,7 @@ namespace lk {
 constexpr int TK = 16;       // k per pipeline stage (16 doubles = one 128-byte swizzle row)
 constexpr int GSTAGES = 4;   // pipeline depth
 constexpr int GEMM_CONSUMER_WARPS = 4;
-constexpr int GEMM_THREADS = 32 * GEMM_CONSUMER_WARPS;  // the TMA producer is thread 0 of consumer warp 0
+constexpr int GEMM_THREADS = 32 * GEMM_CONSUMER_WARPS;  // the TMA producer is an elected lane of consumer warp 0
 constexpr int NS_TILE_BYTES = TN * TK * 8;  // 16384
 constexpr int MS_TILE_BYTES = TM * TK * 8;  // 8192
 constexpr int STAGE_BYTES = NS_TILE_BYTES + MS_TILE_BYTES;
